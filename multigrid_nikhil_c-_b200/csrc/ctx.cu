@@ -1,0 +1,458 @@
+// ctx.cu — context, level table, host<->device movement, cycles.  See ctx.cuh.
+#include "ctx.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "comm.cuh"
+#include "fused.cuh"
+
+namespace mgb {
+
+// ---------------------------------------------------------------------------------
+// slab partition (shared with mg_slab_rows): rank r of R owns node rows
+// [r*N/R, (r+1)*N/R); interior rows are 1..N-1.  Slab boundaries are multiples of
+// N/R on every distributed level, so coarse row I (fine row 2I) and fine row 2I have the
+// same owner and a coarse row never straddles ranks.
+// ---------------------------------------------------------------------------------
+void slab_rows(int level, int rank, int world, int* lo, int* hi)
+{
+    const i64 N = (i64)1 << level;
+    i64 a = (i64)rank * N / world;
+    i64 b = (i64)(rank + 1) * N / world;
+    if (a < 1) a = 1;
+    if (b > N) b = N;
+    if (rank == world - 1) b = N;
+    *lo = (int)a;
+    *hi = (int)b;
+}
+
+static i64 round_up(i64 a, i64 m) { return (a + m - 1) / m * m; }
+
+Ctx::Ctx(const mg_config& c) : cfg(c)
+{
+    MG_REQUIRE(cfg.finest_level >= 1 && cfg.finest_level <= 15, "finest_level must be in 1..15");
+    MG_REQUIRE(cfg.coarsest_level >= 1 && cfg.coarsest_level <= cfg.finest_level,
+               "coarsest_level must be in 1..finest_level");
+    MG_REQUIRE(cfg.dtype == MG_F64 || cfg.dtype == MG_F32, "dtype must be MG_F64 or MG_F32");
+    MG_REQUIRE(cfg.smoother == MG_SMOOTH_JACOBI || cfg.smoother == MG_SMOOTH_RBGS, "unknown smoother");
+    MG_REQUIRE(cfg.world >= 1 && cfg.rank >= 0 && cfg.rank < cfg.world, "bad rank/world");
+    MG_REQUIRE((cfg.world & (cfg.world - 1)) == 0, "world must be a power of two");
+    esize = f64() ? 8 : 4;
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw MgError(MG_ERR_CUDA, std::string("no CUDA device: libmgb200 has no CPU fallback (") +
+                                       cudaGetErrorString(e) + ")");
+    if (cfg.device >= 0) {
+        MG_REQUIRE(cfg.device < ndev, "device ordinal out of range");
+        MG_CK(cudaSetDevice(cfg.device));
+    }
+    MG_CK(cudaGetDevice(&device));
+    MG_CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+
+    // agglomeration threshold: distributed levels need >= 8 rows per rank
+    if (cfg.world > 1) {
+        int min_dist = 3;
+        while (((i64)1 << min_dist) / cfg.world < 8) ++min_dist;
+        aggl_level = cfg.agglomerate_level > 0 ? cfg.agglomerate_level : std::min(cfg.finest_level - 1, 11);
+        aggl_level = std::max(aggl_level, min_dist - 1);
+        aggl_level = std::max(aggl_level, cfg.coarsest_level - 1);
+        MG_REQUIRE(aggl_level < cfg.finest_level || cfg.finest_level < min_dist,
+                   "agglomerate_level must be below finest_level");
+        if (aggl_level >= cfg.finest_level) aggl_level = cfg.finest_level;  // tiny problems: fully replicated
+    } else {
+        aggl_level = cfg.finest_level;
+    }
+
+    levels.resize(cfg.finest_level + 1);
+    const int halo = 1;
+    for (int l = cfg.coarsest_level; l <= cfg.finest_level; ++l) {
+        Level& lv = levels[l];
+        lv.level = l;
+        lv.N = 1 << l;
+        lv.pitch = round_up((i64)lv.N + 1, 32);
+        lv.distributed = (cfg.world > 1 && l > aggl_level);
+        if (lv.distributed) {
+            slab_rows(l, cfg.rank, cfg.world, &lv.own_lo, &lv.own_hi);
+            lv.st_lo = std::max(0, lv.own_lo - halo);
+            lv.st_hi = std::min(lv.N + 1, lv.own_hi + halo);
+            if (cfg.rank == 0) lv.st_lo = 0;
+        } else {
+            lv.own_lo = 1;
+            lv.own_hi = lv.N;
+            lv.st_lo = 0;
+            lv.st_hi = lv.N + 1;
+        }
+        lv.bytes = (size_t)(lv.st_hi - lv.st_lo) * (size_t)lv.pitch * (size_t)esize;
+        for (int k = 0; k < 4; ++k) {
+            cudaError_t ae = cudaMalloc(&lv.alloc[k], lv.bytes);
+            if (ae != cudaSuccess)
+                throw MgError(MG_ERR_ALLOC, std::string("cudaMalloc of level ") + std::to_string(l) + " failed: " +
+                                                cudaGetErrorString(ae));
+            MG_CK(cudaMemsetAsync(lv.alloc[k], 0, lv.bytes, stream));
+            bytes_allocated += lv.bytes;
+        }
+        const i64 off = (i64)lv.st_lo * lv.pitch * esize;
+        lv.u[0] = (char*)lv.alloc[0] - off;
+        lv.u[1] = (char*)lv.alloc[1] - off;
+        lv.f = (char*)lv.alloc[2] - off;
+        lv.r = (char*)lv.alloc[3] - off;
+    }
+    {
+        const Level& top = levels[cfg.finest_level];
+        const int V = f64() ? 2 : 4;
+        partials_cap = (int)(cdiv(top.N, V * kTX) * cdiv(top.st_hi - top.st_lo, kRY)) + 8;
+        MG_CK(cudaMalloc(&d_partials, sizeof(double) * (size_t)partials_cap));
+        MG_CK(cudaMalloc(&d_norm, sizeof(double) * 8));
+        MG_CK(cudaMallocHost(&h_norm, sizeof(double) * 8));
+    }
+    if (cfg.world > 1) comm = comm_create(*this);
+    fused_setup(*this);
+    MG_CK(cudaStreamSynchronize(stream));
+}
+
+Ctx::~Ctx()
+{
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    for (auto& kv : graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (comm) comm_destroy(comm);
+    for (auto& lv : levels)
+        for (int k = 0; k < 4; ++k)
+            if (lv.alloc[k]) cudaFree(lv.alloc[k]);
+    if (d_partials) cudaFree(d_partials);
+    if (d_norm) cudaFree(d_norm);
+    if (h_norm) cudaFreeHost(h_norm);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+Level& Ctx::L(int level)
+{
+    if (level < cfg.coarsest_level || level > cfg.finest_level)
+        throw MgError(MG_ERR_ARG, "level " + std::to_string(level) + " outside [coarsest_level, finest_level]");
+    return levels[level];
+}
+const Level& Ctx::L(int level) const { return const_cast<Ctx*>(this)->L(level); }
+
+void Ctx::sync() { MG_CK(cudaStreamSynchronize(stream)); }
+
+unsigned long long Ctx::parity_mask() const
+{
+    unsigned long long m = 0;
+    for (int l = cfg.coarsest_level; l <= cfg.finest_level; ++l)
+        if (levels[l].cur) m |= 1ull << l;
+    return m;
+}
+void Ctx::set_parity(unsigned long long m)
+{
+    for (int l = cfg.coarsest_level; l <= cfg.finest_level; ++l) levels[l].cur = (m >> l) & 1;
+}
+
+// ---------------------------------------------------------------------------------
+// host <-> device.  Host vectors are full-grid interior vectors in the reference layout
+// (n x n row-major, P:227-228); a rank moves every interior row it stores (owned + halo),
+// so halos are valid after a set without an exchange.
+// ---------------------------------------------------------------------------------
+static char* which_ptr(Level& lv, Ctx::Which w)
+{
+    switch (w) {
+        case Ctx::W_U: return lv.u[lv.cur];
+        case Ctx::W_F: return lv.f;
+        default: return lv.r;
+    }
+}
+
+void Ctx::set_host(int level, Which w, const void* host)
+{
+    MG_REQUIRE(host != nullptr, "null host pointer");
+    Level& lv = L(level);
+    const i64 n = lv.N - 1;
+    const int ya = std::max(lv.st_lo, 1), yb = std::min(lv.st_hi, lv.N);
+    char* dst = which_ptr(lv, w) + ((i64)ya * lv.pitch + 1) * esize;
+    const char* src = (const char*)host + (i64)(ya - 1) * n * esize;
+    MG_CK(cudaMemcpy2DAsync(dst, (size_t)lv.pitch * esize, src, (size_t)n * esize, (size_t)n * esize,
+                            (size_t)(yb - ya), cudaMemcpyHostToDevice, stream));
+    MG_CK(cudaStreamSynchronize(stream));
+}
+
+void Ctx::get_host(int level, Which w, void* host)
+{
+    MG_REQUIRE(host != nullptr, "null host pointer");
+    Level& lv = L(level);
+    const i64 n = lv.N - 1;
+    const int ya = lv.own_lo, yb = lv.own_hi;
+    const char* src = which_ptr(lv, w) + ((i64)ya * lv.pitch + 1) * esize;
+    char* dst = (char*)host + (i64)(ya - 1) * n * esize;
+    MG_CK(cudaMemcpy2DAsync(dst, (size_t)n * esize, src, (size_t)lv.pitch * esize, (size_t)n * esize,
+                            (size_t)(yb - ya), cudaMemcpyDeviceToHost, stream));
+    MG_CK(cudaStreamSynchronize(stream));
+}
+
+void Ctx::zero_u(int level)
+{
+    Level& lv = L(level);
+    MG_CK(cudaMemsetAsync(lv.alloc[lv.cur], 0, lv.bytes, stream));
+}
+
+void Ctx::force_constant(double fval)
+{
+    Level& lv = L(cfg.finest_level);
+    const double h = 1.0 / (double)lv.N;
+    const double b = fval * h * h;  // P:182-184 summed over the six triangles of a node
+    const int ya = std::max(lv.st_lo, 1), yb = std::min(lv.st_hi, lv.N);
+    if (f64()) launch_fill<double>(stream, lc, (double*)lv.f, lv.pitch, lv.N, ya, yb, b);
+    else launch_fill<float>(stream, lc, (float*)lv.f, lv.pitch, lv.N, ya, yb, (float)b);
+    MG_CK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------
+// operators
+// ---------------------------------------------------------------------------------
+template <typename T>
+void Ctx::smooth_t(int level, int nu)
+{
+    Level& lv = L(level);
+    if (nu <= 0) return;
+    if (cfg.smoother == MG_SMOOTH_JACOBI) {
+        // constants exactly as the oracle forms them (P:127, P:138-140)
+        const T om = (T)cfg.omega;
+        const T c0 = (T)(1.0 - (double)om);
+        const T c1 = (T)((double)om / 4.0);
+        int s = 0;
+        while (s < nu) {
+            const int did = fused_jacobi<T>(*this, lv, nu - s, c0, c1);  // temporally blocked sweeps (0 if n/a)
+            if (did > 0) { s += did; continue; }
+            launch_jacobi<T>(stream, lc, (const T*)lv.u[lv.cur], (T*)lv.u[lv.cur ^ 1], (const T*)lv.f,
+                             lv.pitch, lv.N, lv.own_lo, lv.own_hi, c0, c1);
+            lv.cur ^= 1;
+            if (lv.distributed) comm_halo_exchange(*this, lv, lv.u[lv.cur], 1);
+            ++s;
+        }
+    } else {
+        for (int s = 0; s < nu; ++s)
+            for (int colour = 0; colour < 2; ++colour) {
+                launch_rbgs<T>(stream, lc, (T*)lv.u[lv.cur], (const T*)lv.f, lv.pitch, lv.N, lv.own_lo,
+                               lv.own_hi, colour);
+                if (lv.distributed) comm_halo_exchange(*this, lv, lv.u[lv.cur], 1);
+            }
+    }
+    MG_CK(cudaGetLastError());
+}
+
+template <typename T>
+double Ctx::residual_t(int level, bool want_norm, bool store)
+{
+    Level& lv = L(level);
+    const int np = launch_residual<T>(stream, lc, (const T*)lv.u[lv.cur], (const T*)lv.f, (T*)lv.r, lv.pitch,
+                                      lv.N, lv.own_lo, lv.own_hi, want_norm ? d_partials : nullptr, store);
+    MG_CK(cudaGetLastError());
+    if (!want_norm) return 0.0;
+    MG_REQUIRE(!capturing, "norm read-back inside a captured cycle");
+    launch_sum_partials(stream, lc, d_partials, np, d_norm);
+    MG_CK(cudaGetLastError());
+    double sumsq = 0.0;
+    if (lv.distributed) {
+        sumsq = comm_sum(*this, d_norm);  // fixed rank order => same value on every rank
+    } else {
+        MG_CK(cudaMemcpyAsync(h_norm, d_norm, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        MG_CK(cudaStreamSynchronize(stream));
+        sumsq = h_norm[0];
+    }
+    return std::sqrt(sumsq);
+}
+
+template <typename T>
+void Ctx::restrict_t(int fine_level, bool from_rhs)
+{
+    Level& lf = L(fine_level);
+    Level& lcv = L(fine_level - 1);
+    const T w = (T)cfg.restrict_weight;
+    const T* src = (const T*)(from_rhs ? lf.f : lf.r);
+    if (lf.distributed && !from_rhs) comm_halo_exchange(*this, lf, lf.r, 1);  // r of the neighbour's edge row
+    if (lf.distributed && !lcv.distributed) {
+        // agglomeration: every rank restricts its slab of coarse rows, then all-gathers
+        int lo, hi;
+        slab_rows(lcv.level, cfg.rank, cfg.world, &lo, &hi);
+        if (!from_rhs) { lcv.cur = 0; }
+        launch_restrict<T>(stream, lc, src, lf.pitch, (T*)lcv.f, from_rhs ? nullptr : (T*)lcv.u[lcv.cur],
+                           lcv.pitch, lcv.N, lo, hi, w);
+        MG_CK(cudaGetLastError());
+        comm_allgather_rows(*this, lcv, lcv.f);
+        if (!from_rhs) MG_CK(cudaMemsetAsync(lcv.alloc[lcv.cur], 0, lcv.bytes, stream));
+        return;
+    }
+    if (!from_rhs) lcv.cur = 0;  // fixed buffer for the zero guess keeps graph replays valid
+    launch_restrict<T>(stream, lc, src, lf.pitch, (T*)lcv.f, from_rhs ? nullptr : (T*)lcv.u[lcv.cur], lcv.pitch,
+                       lcv.N, lcv.own_lo, lcv.own_hi, w);
+    MG_CK(cudaGetLastError());
+    if (lcv.distributed && !from_rhs) {
+        // halo rows of the zero guess: clear them too
+        comm_zero_halo(*this, lcv, lcv.u[lcv.cur]);
+    }
+}
+
+template <typename T>
+void Ctx::prolong_t(int fine_level, bool add)
+{
+    Level& lf = L(fine_level);
+    Level& lcv = L(fine_level - 1);
+    // coarse halos are valid after every smoothing sweep; every stored interior fine row
+    // (owned + halo) can therefore be prolonged locally, no exchange needed afterwards.
+    const int ya = std::max(lf.st_lo, 1), yb = std::min(lf.st_hi, lf.N);
+    launch_prolong<T>(stream, lc, (const T*)lcv.u[lcv.cur], lcv.pitch, (T*)lf.u[lf.cur], lf.pitch, lf.N, ya, yb,
+                      add);
+    MG_CK(cudaGetLastError());
+}
+
+void Ctx::smooth(int level, int nu) { f64() ? smooth_t<double>(level, nu) : smooth_t<float>(level, nu); }
+double Ctx::residual(int level, bool want_norm, bool store)
+{
+    return f64() ? residual_t<double>(level, want_norm, store) : residual_t<float>(level, want_norm, store);
+}
+void Ctx::restrict_to(int fine_level, bool from_rhs)
+{
+    MG_REQUIRE(fine_level > cfg.coarsest_level, "no coarser level below coarsest_level");
+    f64() ? restrict_t<double>(fine_level, from_rhs) : restrict_t<float>(fine_level, from_rhs);
+}
+void Ctx::prolong(int fine_level, bool add)
+{
+    MG_REQUIRE(fine_level > cfg.coarsest_level, "no coarser level below coarsest_level");
+    f64() ? prolong_t<double>(fine_level, add) : prolong_t<float>(fine_level, add);
+}
+
+// ---------------------------------------------------------------------------------
+// cycles.  cycle_rec mirrors vcyclemultigrid P:575-627 line by line.
+// ---------------------------------------------------------------------------------
+void Ctx::cycle_rec(int level, int nu1, int nu2, int gamma)
+{
+    if (fused_cycle_level(*this, level, nu1, nu2, gamma)) return;  // fused pre/post kernels or coarse tail
+    smooth(level, nu1);                                     // P:581
+    if (level <= cfg.coarsest_level) {                      // P:583
+        smooth(level, nu2);                                 // P:585
+        return;
+    }
+    residual(level, false, true);                           // P:604-608
+    restrict_to(level, false);                              // P:611, P:613
+    const int reps = (level - 1 <= cfg.coarsest_level) ? 1 : std::max(1, gamma);
+    for (int g = 0; g < reps; ++g) cycle_rec(level - 1, nu1, nu2, gamma);  // P:617
+    prolong(level, true);                                   // P:620-624
+    smooth(level, nu2);                                     // P:625
+}
+
+void Ctx::cycle(int level, int nu1, int nu2, int gamma)
+{
+    L(level);
+    MG_REQUIRE(nu1 >= 0 && nu2 >= 0 && gamma >= 1, "nu1, nu2 >= 0 and gamma >= 1 required");
+    if (!(cfg.flags & MG_GRAPH) || capturing) {
+        cycle_rec(level, nu1, nu2, gamma);
+        return;
+    }
+    auto key = std::make_tuple(level, nu1, nu2, gamma, parity_mask());
+    auto it = graphs.find(key);
+    if (it == graphs.end()) {
+        GraphEntry ge;
+        const long long before = lc.n;
+        cudaGraph_t g = nullptr;
+        MG_CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        capturing = true;
+        try {
+            cycle_rec(level, nu1, nu2, gamma);
+        } catch (...) {
+            capturing = false;
+            cudaStreamEndCapture(stream, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        capturing = false;
+        MG_CK(cudaStreamEndCapture(stream, &g));
+        ge.kernels = lc.n - before;
+        ge.parity_after = parity_mask();
+        cudaError_t ie = cudaGraphInstantiate(&ge.exec, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) throw MgError(MG_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+        it = graphs.emplace(key, ge).first;
+        lc.n = before;  // counted again at launch below
+    }
+    MG_CK(cudaGraphLaunch(it->second.exec, stream));
+    lc.n += it->second.kernels;
+    ++graph_launches;
+    set_parity(it->second.parity_after);
+}
+
+void Ctx::fmg(int cycles, int nu1, int nu2)
+{
+    MG_REQUIRE(cycles >= 1, "cycles_per_level >= 1 required");
+    for (int l = cfg.finest_level; l > cfg.coarsest_level; --l) restrict_to(l, true);  // P:641
+    zero_u(cfg.coarsest_level);                                                          // P:630
+    for (int i = 0; i < cycles; ++i) cycle(cfg.coarsest_level, nu1, nu2, 1);             // P:635-637
+    for (int l = cfg.coarsest_level + 1; l <= cfg.finest_level; ++l) {
+        prolong(l, false);                                                               // P:645
+        for (int i = 0; i < cycles; ++i) cycle(l, nu1, nu2, 1);                          // P:646-648
+    }
+}
+
+int Ctx::solve(double rtol, int max_cycles, int nu1, int nu2, int gamma, double* relres, double* history)
+{
+    const int top = cfg.finest_level;
+    const double r0 = residual(top, true, false);
+    if (history) history[0] = r0;
+    int k = 0;
+    double rk = r0;
+    while (k < max_cycles) {
+        cycle(top, nu1, nu2, gamma);
+        ++k;
+        rk = residual(top, true, false);
+        if (history) history[k] = rk;
+        if (r0 == 0.0 || rk <= rtol * r0) break;
+    }
+    if (relres) *relres = (r0 > 0.0) ? rk / r0 : 0.0;
+    return k;
+}
+
+float Ctx::time_op(int op, int level, int reps)
+{
+    MG_REQUIRE(reps >= 1, "reps >= 1 required");
+    L(level);
+    cudaEvent_t e0, e1;
+    MG_CK(cudaEventCreate(&e0));
+    MG_CK(cudaEventCreate(&e1));
+    auto run = [&]() {
+        switch (op) {
+            case MG_OP_SMOOTH1: smooth(level, 1); break;
+            case MG_OP_SMOOTH2: smooth(level, 2); break;
+            case MG_OP_RESIDUAL: residual(level, false, true); break;
+            case MG_OP_RESIDUAL_NORM: {
+                Level& lv = L(level);
+                if (f64()) launch_residual<double>(stream, lc, (const double*)lv.u[lv.cur], (const double*)lv.f, (double*)lv.r, lv.pitch, lv.N, lv.own_lo, lv.own_hi, d_partials, false);
+                else launch_residual<float>(stream, lc, (const float*)lv.u[lv.cur], (const float*)lv.f, (float*)lv.r, lv.pitch, lv.N, lv.own_lo, lv.own_hi, d_partials, false);
+                break;
+            }
+            case MG_OP_RESTRICT: restrict_to(level, false); break;
+            case MG_OP_PROLONG: prolong(level, true); break;
+            case MG_OP_PRE_FUSED:
+                if (!fused_time_hook(*this, level, true)) throw MgError(MG_ERR_STATE, "fused pre-smoothing kernel not available for this level/config");
+                break;
+            case MG_OP_POST_FUSED:
+                if (!fused_time_hook(*this, level, false)) throw MgError(MG_ERR_STATE, "fused post-smoothing kernel not available for this level/config");
+                break;
+            default: throw MgError(MG_ERR_ARG, "unknown op");
+        }
+    };
+    run();  // warm
+    MG_CK(cudaStreamSynchronize(stream));
+    MG_CK(cudaEventRecord(e0, stream));
+    for (int i = 0; i < reps; ++i) run();
+    MG_CK(cudaEventRecord(e1, stream));
+    MG_CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    MG_CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ms;
+}
+
+}  // namespace mgb

@@ -1,0 +1,17 @@
+// fused.cuh — fused / temporally blocked kernels (MG_FUSED) and the shared-memory
+// coarse tail (MG_COARSE_TAIL).  Implemented in fused.cu.
+#pragma once
+
+#include "ctx.cuh"
+
+namespace mgb {
+
+void fused_setup(Ctx& ctx);
+// run up to `remaining` temporally blocked Jacobi sweeps on level lv; returns the number done (0 = not applicable)
+template <typename T> int fused_jacobi(Ctx& ctx, Level& lv, int remaining, T c0, T c1);
+// run one whole cycle visit of `level` with fused kernels; false = caller runs the unfused sequence
+bool fused_cycle_level(Ctx& ctx, int level, int nu1, int nu2, int gamma);
+// one launch of the fused pre- (true) or post-smoothing (false) kernel for timing; false if unavailable
+bool fused_time_hook(Ctx& ctx, int level, bool pre);
+
+}  // namespace mgb

@@ -172,10 +172,10 @@ class Oracle:
         return out
 
     # -- cycles ------------------------------------------------------------
-    def vcyclemultigrid(self, vec_h, f_h, params: Params | None = None):
-        """P:575-627; returns the new iterate."""
+    def vcyclemultigrid(self, vec_h, f_h, params: Params | None = None, inplace: bool = False):
+        """P:575-627; returns the new iterate (inplace=True overwrites vec_h, as P:581 does)."""
         p = (params or Params()).c()
-        out = np.array(vec_h, copy=True)
+        out = vec_h if inplace else np.array(vec_h, copy=True)
         self._chk(out, f_h)
         self._f("mgo_vcyclemultigrid", out)(_ptr(out), _ptr(f_h), level_of(_side(out)), ctypes.byref(p))
         return out

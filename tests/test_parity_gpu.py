@@ -1,0 +1,221 @@
+"""GPU parity tests: every CUDA entry point of libmgb200.so (called through the C ABI) is
+compared with the CPU oracle on identical seeded inputs.  The library is built with
+--fmad=false and evaluates the point formulas in the oracle's order, so the bar is
+BIT-EXACT for every operator and whole cycles (tighter than the north star's 1e-12
+relative); only the residual norm (a reduction) carries a tolerance, written below."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import assert_bitwise, rand_vec
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [np.float64, np.float32]
+NORM_RTOL = 1e-13   # GPU tree reduction vs oracle's sequential double sum
+
+
+def make(mgb, level, dtype=np.float64, **kw):
+    kw.setdefault("coarsest_level", 1)
+    return mgb.Multigrid(level, dtype=dtype, **kw)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("level", [1, 2, 3, 4, 5, 7, 8, 9, 10])
+def test_jacobi_iterates_bitwise(mgb, orc, level, dtype):
+    x, b = rand_vec(level, dtype, 1), rand_vec(level, dtype, 2, 1e-3)
+    with make(mgb, level, dtype, coarsest_level=min(level, 1)) as mg:
+        for nu in (1, 2, 3, 5):
+            mg.set_u(level, x)
+            mg.set_rhs(level, b)
+            mg.smooth(level, nu)
+            assert_bitwise(mg.get_u(level), orc.jacobirelaxation(x, b, nu), f"jacobi L{level} nu={nu}")
+        # the reference-shaped host call (P:125): mutates v and returns it
+        v = x.copy()
+        out = mg.jacobirelaxation(v, b, 4)
+        assert_bitwise(out, orc.jacobirelaxation(x, b, 4), "host jacobirelaxation")
+        assert_bitwise(v, out, "v mutated in place (P:146)")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("level", [1, 2, 3, 5, 8, 10])
+def test_rbgs_bitwise(mgb, orc, level, dtype):
+    x, b = rand_vec(level, dtype, 3), rand_vec(level, dtype, 4, 1e-3)
+    with make(mgb, level, dtype, smoother="rbgs") as mg:
+        for nu in (1, 2, 3):
+            mg.set_u(level, x)
+            mg.set_rhs(level, b)
+            mg.smooth(level, nu)
+            assert_bitwise(mg.get_u(level), orc.rbgs(x, b, nu), f"rbgs L{level} nu={nu}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("level", [1, 2, 3, 6, 9, 10])
+def test_residual_and_norm(mgb, orc, level, dtype):
+    x, b = rand_vec(level, dtype, 5), rand_vec(level, dtype, 6)
+    with make(mgb, level, dtype) as mg:
+        mg.set_u(level, x)
+        mg.set_rhs(level, b)
+        nrm = mg.residual(level, norm=True)
+        r = orc.residual(x, b)
+        assert_bitwise(mg.get_r(level), r, f"residual L{level}")
+        assert nrm == pytest.approx(orc.norm2(r), rel=NORM_RTOL if dtype == np.float64 else 1e-12)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("level", [2, 3, 4, 6, 9, 10])
+def test_transfer_operators_bitwise(mgb, orc, level, dtype):
+    fine, coarse = rand_vec(level, dtype, 7), rand_vec(level - 1, dtype, 8)
+    with make(mgb, level, dtype) as mg:
+        assert_bitwise(mg.restriction2d(fine), orc.restriction2d(fine), "restriction2d")
+        assert_bitwise(mg.interpolation2d(coarse), orc.interpolation2d(coarse), "interpolation2d")
+        # resident: prolong + correct (P:620-624)
+        mg.set_u(level, fine)
+        mg.set_u(level - 1, coarse)
+        mg.prolong_correct(level)
+        assert_bitwise(mg.get_u(level), orc.prolong_correct(coarse, fine), "prolong_correct")
+        # restriction of the RHS for FMG (P:641) and the zero coarse guess (P:613)
+        mg.set_rhs(level, fine)
+        mg.restrict_rhs(level)
+        assert_bitwise(mg.get_rhs(level - 1), orc.restriction2d(fine), "restrict_rhs")
+        mg.set_u(level, fine)
+        mg.set_rhs(level, rand_vec(level, dtype, 9))
+        mg.residual(level)
+        mg.restrict(level)
+        assert_bitwise(mg.get_rhs(level - 1), orc.restriction2d(orc.residual(fine, rand_vec(level, dtype, 9))), "restrict(residual)")
+        assert not mg.get_u(level - 1).any()
+
+
+def test_literal_fd_weight(mgb, orc):
+    level = 6
+    fine = rand_vec(level, np.float64, 10)
+    with make(mgb, level, restrict_weight=1.0 / 16.0) as mg:
+        assert_bitwise(mg.restriction2d(fine), orc.restriction2d(fine, w=1.0 / 16.0), "restriction2d 1/16")
+
+
+CYCLES = [  # smoother, nu1, nu2, gamma, coarsest
+    ("jacobi", 2, 2, 1, 1), ("jacobi", 1, 1, 1, 1), ("jacobi", 2, 1, 1, 1), ("jacobi", 3, 0, 1, 2),
+    ("jacobi", 2, 2, 2, 1), ("rbgs", 2, 2, 1, 1), ("rbgs", 1, 1, 2, 1), ("jacobi", 10, 10, 1, 4),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("smoother,nu1,nu2,gamma,coarsest", CYCLES)
+@pytest.mark.parametrize("level", [4, 7, 9])
+def test_cycles_bitwise_all_flag_combinations(mgb, orc, level, dtype, smoother, nu1, nu2, gamma, coarsest):
+    """vcyclemultigrid P:575-627 (gamma=2: W): three consecutive cycles, with and without
+    CUDA graphs / fused kernels / the coarse tail -- all must equal the oracle bit for bit."""
+    x, b = rand_vec(level, dtype, 21), rand_vec(level, dtype, 22, 1e-3)
+    p = oracle.Params(coarsest_level=coarsest, nu1=nu1, nu2=nu2, gamma=gamma, smoother=1 if smoother == "rbgs" else 0,
+                      nthreads=4)
+    want = [x]
+    for _ in range(3):
+        want.append(orc.vcyclemultigrid(want[-1], b, p))
+    for graph, fused, tail in ((False, False, False), (True, False, False), (False, True, False),
+                               (False, False, True), (True, True, True)):
+        with make(mgb, level, dtype, coarsest_level=coarsest, smoother=smoother, graph=graph, fused=fused,
+                  coarse_tail=tail) as mg:
+            mg.set_u(level, x)
+            mg.set_rhs(level, b)
+            for k in range(3):
+                mg.cycle(level, nu1, nu2, gamma)
+                assert_bitwise(mg.get_u(level), want[k + 1], f"cycle {k + 1} graph={graph} fused={fused} tail={tail}")
+            # host-vector entry point (one call == one reference call)
+            assert_bitwise(mg.vcyclemultigrid(x, b, nu1, nu2, gamma), want[1], "host vcyclemultigrid")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("smoother", ["jacobi", "rbgs"])
+def test_fullmultigrid_bitwise(mgb, orc, dtype, smoother):
+    level = 8
+    b = rand_vec(level, dtype, 31, 1e-3)
+    for cycles, nu, coarsest in ((1, 2, 1), (2, 2, 1), (3, 10, 5)):
+        p = oracle.Params(coarsest_level=coarsest, nu1=nu, nu2=nu, smoother=1 if smoother == "rbgs" else 0, nthreads=4)
+        with make(mgb, level, dtype, coarsest_level=coarsest, smoother=smoother) as mg:
+            assert_bitwise(mg.fullmultigrid(b, cycles, nu, nu), orc.fullmultigrid(b, cycles, p), f"fmg c={cycles}")
+
+
+@pytest.mark.parametrize("smoother,gamma,cycles,relres", [("jacobi", 1, 13, 7.287e-09), ("rbgs", 1, 7, 4.102e-09),
+                                                           ("jacobi", 2, 10, 3.803e-09), ("rbgs", 2, 5, 1.317e-09)])
+def test_config0_solve_257_matches_reference_history(mgb, orc, smoother, gamma, cycles, relres):
+    """BASELINE.json configs[0]: 257^2 fp64 V(2,2) to 1e-8: same cycle count,
+    same residual history as the oracle to 1e-10 relative, same iterate bit for bit."""
+    level = 8
+    with make(mgb, level, smoother=smoother) as mg:
+        b = mg.globalforcefunction(4.0)
+        assert_bitwise(b, orc.globalforcefunction(level), "globalforcefunction")
+        mg.zero_u(level)
+        k, rel, hist = mg.solve(1e-8, 60, 2, 2, gamma)
+        p = oracle.Params(smoother=1 if smoother == "rbgs" else 0, gamma=gamma, nthreads=4)
+        u, ko, ho = orc.solve(np.zeros_like(b), b, 1e-8, 60, p)
+        assert k == ko == cycles
+        assert rel == pytest.approx(relres, rel=2e-3)
+        assert np.allclose(hist, ho, rtol=1e-10, atol=0)
+        assert_bitwise(mg.get_u(level), u, "solution")
+
+
+def test_golden_fixtures(mgb):
+    """Committed oracle outputs (tests/golden/oracle_golden.npz, made by make_golden.py)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.npz"))
+    meta = json.loads(str(g["meta"]))
+    for case in meta["cases"]:
+        level, dtype = case["level"], np.dtype(case["dtype"])
+        x = rand_vec(level, dtype, case["seed_u"])
+        b = rand_vec(level, dtype, case["seed_b"], case["scale_b"])
+        smoother = "rbgs" if (case["smoother"] == 1 or case["op"] == "rbgs2") else "jacobi"
+        with make(mgb, level + (1 if case["op"] == "prolong" else 0), dtype, smoother=smoother) as mg:
+            op = case["op"]
+            if op in ("jacobi3", "rbgs2"):
+                mg.set_u(level, x); mg.set_rhs(level, b); mg.smooth(level, 3 if op == "jacobi3" else 2)
+                got = mg.get_u(level)
+            elif op == "residual":
+                mg.set_u(level, x); mg.set_rhs(level, b); mg.residual(level)
+                got = mg.get_r(level)
+            elif op == "restrict":
+                got = mg.restriction2d(x)
+            elif op == "prolong":
+                got = mg.interpolation2d(x)
+            elif op == "vcycle":
+                got = mg.vcyclemultigrid(x, b, 2, 2, case["gamma"])
+            else:
+                got = mg.fullmultigrid(b, 1, 2, 2)
+            assert_bitwise(got, g[case["name"]], case["name"])
+
+
+def test_config1_full_size_4097_vcycle(mgb, orc):
+    """BASELINE.json configs[1] at full size: one V(2,2) on 4097^2 fp64 equals the oracle
+    bit for bit; plus size-independent properties (linearity of the cycle in (u, b), and
+    residual reduction factor of C.3)."""
+    level = 12
+    n = (1 << level) - 1
+    b = (1.0 / 4096.0) ** 2 * np.random.default_rng(1234).uniform(-1, 1, n * n)
+    p = oracle.Params(nthreads=orc.max_threads())
+    with make(mgb, level) as mg:
+        mg.set_rhs(level, b)
+        mg.zero_u(level)
+        r0 = mg.residual(level, norm=True)
+        mg.cycle(level, 2, 2, 1)
+        r1 = mg.residual(level, norm=True)
+        u1 = mg.get_u(level)
+        assert_bitwise(u1, orc.vcyclemultigrid(np.zeros(n * n), b, p), "V(2,2) at 4097^2")
+        assert 0.05 < r1 / r0 < 0.12          # first factor for a random RHS (C.3: 0.084 at 257^2)
+        # linearity: cycle(0, 2b) == 2 * cycle(0, b) exactly (scaling by 2 is exact)
+        mg.set_rhs(level, 2.0 * b)
+        mg.zero_u(level)
+        mg.cycle(level, 2, 2, 1)
+        assert_bitwise(mg.get_u(level), 2.0 * u1, "linearity in b")
+
+
+def test_errors_are_loud(mgb):
+    with make(mgb, 5) as mg:
+        with pytest.raises(mgb.capi.MgError):
+            mg.smooth(9, 1)
+        with pytest.raises(mgb.capi.MgError):
+            mg.restrict(1)
+        with pytest.raises(ValueError):
+            mg.set_u(5, np.zeros(10))
+    with pytest.raises(mgb.capi.MgError):
+        mgb.Multigrid(3, coarsest_level=4)
