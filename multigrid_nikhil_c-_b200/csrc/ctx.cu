@@ -104,7 +104,7 @@ Ctx::Ctx(const mg_config& c) : cfg(c)
     {
         const Level& top = levels[cfg.finest_level];
         const int V = f64() ? 2 : 4;
-        partials_cap = (int)(cdiv(top.N, V * kTX) * cdiv(top.st_hi - top.st_lo, kRY)) + 8;
+        partials_cap = (int)(cdiv(top.N, V * kTX) * cdiv(top.st_hi - top.st_lo, 2)) + 8;
         MG_CK(cudaMalloc(&d_partials, sizeof(double) * (size_t)partials_cap));
         MG_CK(cudaMalloc(&d_norm, sizeof(double) * 8));
         MG_CK(cudaMallocHost(&h_norm, sizeof(double) * 8));

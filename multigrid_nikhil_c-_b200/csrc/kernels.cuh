@@ -10,7 +10,7 @@
 namespace mgb {
 
 constexpr int kTX = 128;   // threads per block along x  (=> 256 fp64 / 512 fp32 columns per block)
-constexpr int kRY = 32;    // rows marched per block
+constexpr int kRYMax = 32; // max rows marched per block (fewer on small levels, see pick_ry)
 
 struct LaunchCounter { long long n = 0; };
 
@@ -21,13 +21,13 @@ struct LaunchCounter { long long n = 0; };
 template <typename T>
 __global__ void __launch_bounds__(kTX)
 k_jacobi(const T* __restrict__ u, T* __restrict__ out, const T* __restrict__ f,
-         i64 pitch, int N, int ya, int yb, T c0, T c1)
+         i64 pitch, int N, int ya, int yb, int ry, T c0, T c1)
 {
     constexpr int V = Vec<T>::N;
     const int c = V * (blockIdx.x * kTX + threadIdx.x);
     if (c >= N) return;
-    const int y0 = ya + blockIdx.y * kRY;
-    const int y1 = min(y0 + kRY, yb);
+    const int y0 = ya + blockIdx.y * ry;
+    const int y1 = min(y0 + ry, yb);
     if (y0 >= y1) return;
 
     const T* pu = u + (i64)(y0 - 1) * pitch + c;
@@ -71,13 +71,13 @@ k_jacobi(const T* __restrict__ u, T* __restrict__ out, const T* __restrict__ f,
 // ---------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kTX)
-k_rbgs(T* __restrict__ u, const T* __restrict__ f, i64 pitch, int N, int ya, int yb, int colour)
+k_rbgs(T* __restrict__ u, const T* __restrict__ f, i64 pitch, int N, int ya, int yb, int ry, int colour)
 {
     constexpr int V = Vec<T>::N;
     const int c = V * (blockIdx.x * kTX + threadIdx.x);
     if (c >= N) return;
-    const int y0 = ya + blockIdx.y * kRY;
-    const int y1 = min(y0 + kRY, yb);
+    const int y0 = ya + blockIdx.y * ry;
+    const int y1 = min(y0 + ry, yb);
     if (y0 >= y1) return;
 
     // NOTE: rows are NOT marched with a register window here: row y-1's points of the
@@ -112,12 +112,12 @@ k_rbgs(T* __restrict__ u, const T* __restrict__ f, i64 pitch, int N, int ya, int
 template <typename T, bool STORE>
 __global__ void __launch_bounds__(kTX)
 k_residual(const T* __restrict__ u, const T* __restrict__ f, T* __restrict__ r,
-           i64 pitch, int N, int ya, int yb, double* __restrict__ partials)
+           i64 pitch, int N, int ya, int yb, int ry, double* __restrict__ partials)
 {
     constexpr int V = Vec<T>::N;
     const int c = V * (blockIdx.x * kTX + threadIdx.x);
-    const int y0 = ya + blockIdx.y * kRY;
-    const int y1 = min(y0 + kRY, yb);
+    const int y0 = ya + blockIdx.y * ry;
+    const int y1 = min(y0 + ry, yb);
     double acc = 0.0;
     if (c < N && y0 < y1) {
         const T* pu = u + (i64)(y0 - 1) * pitch + c;
@@ -323,13 +323,23 @@ k_repack(T* __restrict__ padded, i64 pitch, T* __restrict__ flat, int N, int ya,
 // ---------------------------------------------------------------------------------
 inline unsigned cdiv(i64 a, i64 b) { return (unsigned)((a + b - 1) / b); }
 
+// rows marched per block: 32 on big levels (halo rows re-read: 6%), fewer on small levels so
+// that the grid still has >= ~4 blocks per SM (a 32-row march is a 32-deep latency chain)
+inline int pick_ry(int rows, unsigned blocks_x)
+{
+    const i64 ry = (i64)rows * blocks_x / 592;
+    return (int)(ry < 2 ? 2 : (ry > kRYMax ? kRYMax : ry));
+}
+
 template <typename T>
 inline void launch_jacobi(cudaStream_t st, LaunchCounter& lc, const T* u, T* out, const T* f,
                           i64 pitch, int N, int ya, int yb, T c0, T c1)
 {
     if (ya >= yb) return;
-    dim3 grid(cdiv(N, Vec<T>::N * kTX), cdiv(yb - ya, kRY));
-    k_jacobi<T><<<grid, kTX, 0, st>>>(u, out, f, pitch, N, ya, yb, c0, c1);
+    const unsigned gx = cdiv(N, Vec<T>::N * kTX);
+    const int ry = pick_ry(yb - ya, gx);
+    dim3 grid(gx, cdiv(yb - ya, ry));
+    k_jacobi<T><<<grid, kTX, 0, st>>>(u, out, f, pitch, N, ya, yb, ry, c0, c1);
     ++lc.n;
 }
 
@@ -338,8 +348,10 @@ inline void launch_rbgs(cudaStream_t st, LaunchCounter& lc, T* u, const T* f, i6
                         int ya, int yb, int colour)
 {
     if (ya >= yb) return;
-    dim3 grid(cdiv(N, Vec<T>::N * kTX), cdiv(yb - ya, kRY));
-    k_rbgs<T><<<grid, kTX, 0, st>>>(u, f, pitch, N, ya, yb, colour);
+    const unsigned gx = cdiv(N, Vec<T>::N * kTX);
+    const int ry = pick_ry(yb - ya, gx);
+    dim3 grid(gx, cdiv(yb - ya, ry));
+    k_rbgs<T><<<grid, kTX, 0, st>>>(u, f, pitch, N, ya, yb, ry, colour);
     ++lc.n;
 }
 
@@ -349,9 +361,11 @@ inline int launch_residual(cudaStream_t st, LaunchCounter& lc, const T* u, const
                            i64 pitch, int N, int ya, int yb, double* partials, bool store)
 {
     if (ya >= yb) return 0;
-    dim3 grid(cdiv(N, Vec<T>::N * kTX), cdiv(yb - ya, kRY));
-    if (store) k_residual<T, true><<<grid, kTX, 0, st>>>(u, f, r, pitch, N, ya, yb, partials);
-    else k_residual<T, false><<<grid, kTX, 0, st>>>(u, f, r, pitch, N, ya, yb, partials);
+    const unsigned gx = cdiv(N, Vec<T>::N * kTX);
+    const int ry = pick_ry(yb - ya, gx);
+    dim3 grid(gx, cdiv(yb - ya, ry));
+    if (store) k_residual<T, true><<<grid, kTX, 0, st>>>(u, f, r, pitch, N, ya, yb, ry, partials);
+    else k_residual<T, false><<<grid, kTX, 0, st>>>(u, f, r, pitch, N, ya, yb, ry, partials);
     ++lc.n;
     return partials ? (int)(grid.x * grid.y) : 0;
 }
