@@ -285,6 +285,15 @@ def run_ours(args, rank, world, local_rank):
                          "GBps": s_per_pt * esize * pts / (t * 1e-3) / 1e9,
                          "frac_of_peak": s_per_pt * esize * pts / (t * 1e-3) / 1e9 / peak,
                          "effective_unfused_GBps": unfused * esize * pts / (t * 1e-3) / 1e9}
+    # cumulative cost of the cycle from each level down (level_ms[l] - level_ms[l-1] = cost of level l's visit)
+    level_ms = {}
+    if world == 1:
+        for l in range(max(2, min(6, level)), level + 1):
+            try:
+                mg.time_cycle(l, nu1, nu2, gamma, 3)
+                level_ms[str(l)] = mg.time_cycle(l, nu1, nu2, gamma, 20) / 20
+            except capi.MgError:
+                pass
     dom = "jacobi_sweep"
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -296,7 +305,8 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "kernel": "k_jacobi (one weighted-Jacobi sweep, finest level)",
                 "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["GBps"] / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
-                "ms_per_launch": kernels[dom]["ms"], "kernels": kernels}
+                "ms_per_launch": kernels[dom]["ms"], "kernels": kernels,
+                "cycle_ms_from_level_down": level_ms}
 
     # ---- end to end through the reference-shaped host call (P:575 on host vectors) ----
     mg.set_rhs(level, f_host)

@@ -20,6 +20,15 @@
 // Gauss-Seidel (then NS = 2 x sweeps).  Every point value is produced by the same
 // expression, in the same order, as in the unfused kernels (common.cuh), so results are
 // bit-identical to them and to the oracle.
+//
+// The kernel is instruction-issue sensitive (profiles/r01_v2_*: 69 % issue utilisation,
+// half of it integer work), hence:
+//  - the ring has 12 slots = 4 blocks of 3; the row loop is unrolled by 3 so that window
+//    rotation is pure register renaming and every ring address is (block pointer +
+//    compile-time constant);
+//  - Dirichlet masking is a warp-uniform branch taken only by strips / rows that touch the
+//    boundary; interior warps execute no mask instructions at all;
+//  - global pointers for prefetch and store advance by one pitch per step.
 #pragma once
 
 #include "common.cuh"
@@ -28,7 +37,8 @@ namespace mgb {
 
 enum { MODE_SWEEPS = 0, MODE_PRE = 1, MODE_POST = 2 };
 
-constexpr int kStreamWarps = 4;  // warps (independent work items) per CTA
+constexpr int kStreamWarps = 1;  // warps (independent work items) per CTA: 1 => occupancy is bounded by registers, not by ring smem
+constexpr int kRingSlots = 12;   // 4 blocks x 3 slots
 
 template <typename T, int NS, int MODE>
 struct StreamCfg {
@@ -40,11 +50,15 @@ struct StreamCfg {
     static constexpr int OUTW = 32 * V - 2 * V * HLANES;                                // output columns per strip
     static constexpr int HT = NS + (MODE == MODE_PRE ? 2 : (MODE == MODE_POST ? 1 : 0));  // rows needed above
     static constexpr int HB = NS + (MODE == MODE_PRE ? 2 : 0);                          // rows needed below
-    static constexpr int D = (NS >= 4) ? 5 : 6;                                         // prefetch distance (rows)
-    static constexpr int DEPTH = D + NS + 3;                                            // ring slots
+    static constexpr int DEPTH = kRingSlots;
+    static constexpr int D = DEPTH - NS - 3;                                            // prefetch distance (rows)
     static constexpr int NW = NS + (MODE == MODE_PRE ? 1 : 0);                          // register windows of u_s
-    static constexpr int SLOT_ELEMS = 32 * V * 2 + (MODE == MODE_POST ? 32 * (V / 2) : 0);
-    static constexpr size_t SMEM_BYTES = (size_t)kStreamWarps * DEPTH * SLOT_ELEMS * sizeof(T);
+    // slot: [u: 32 V][f: 32 V]; POST keeps the coarse rows in a second, half-rate ring
+    static constexpr int SLOT_ELEMS = 32 * V * 2;
+    static constexpr int CSLOT_ELEMS = 32 * (V / 2);
+    static constexpr int WARP_ELEMS = DEPTH * SLOT_ELEMS + (MODE == MODE_POST ? DEPTH * CSLOT_ELEMS : 0);
+    static constexpr size_t SMEM_BYTES = (size_t)kStreamWarps * WARP_ELEMS * sizeof(T);
+    static_assert(D >= 3, "ring too shallow");
 };
 
 template <typename T>
@@ -89,44 +103,65 @@ struct Streamer {
     static constexpr int V = C::V;
     static constexpr int H = V / 2;
     static constexpr unsigned FULL = 0xffffffffu;
+    static constexpr int BLK = 3 * C::SLOT_ELEMS;    // elements per ring block (3 slots)
+    static constexpr int CBLK = 3 * C::CSLOT_ELEMS;
 
     const StreamArgs<T>& a;
-    T* ring;      // this lane's 16 bytes of slot 0 (u part)
-    int lane, c;  // lane id, first column
-    int out_lo, out_hi, y0, y1;
-    int slot;     // ring slot of the row arriving in the current step
+    T* ring;       // this lane's 16 bytes of slot 0 (u part)
+    T* cring;      // POST: this lane's 8 bytes of coarse slot 0
+    T* blk[4];     // blk[j] = ring block (q + j) & 3 for the current outer iteration q
+    T* cblk[4];
+    int c;         // first column of this lane
+    int y0, y1;
+    bool lane_ld, lane_ldc, lane_st, edge;  // per-lane load / store flags; warp-uniform "strip touches a boundary column"
+    bool cz[V];    // column must hold zero (Dirichlet ring / beyond the grid)
+    const T* g_u;  // global prefetch pointers (row of the next prefetch, this lane's column)
+    const T* g_f;
+    T* g_o;        // output pointer of the row the last smoothing stage produces in this step
 
-    // register windows: W[s][phase slot][k], neighbours of each row
     T W[C::NW > 0 ? C::NW : 1][3][V];
     T WL[C::NW > 0 ? C::NW : 1][3], WR[C::NW > 0 ? C::NW : 1][3];
     T R[3][V], RL[3];  // PRE: residual window (left neighbours only)
 
     __device__ __forceinline__ Streamer(const StreamArgs<T>& a_) : a(a_) {}
 
-    __device__ __forceinline__ T* slot_u(int s) const { return ring + (size_t)s * C::SLOT_ELEMS; }
-    __device__ __forceinline__ T* slot_f(int s) const { return ring + (size_t)s * C::SLOT_ELEMS + 32 * V; }
-    __device__ __forceinline__ T* slot_c(int s) const { return ring + (size_t)s * C::SLOT_ELEMS + 64 * V - lane * V + lane * H; }
-    __device__ __forceinline__ int slot_back(int k) const { int s = slot - k; return s < 0 ? s + C::DEPTH : s; }
-
-    // prefetch row y into ring slot s (always commits exactly one group)
-    __device__ __forceinline__ void issue(int y, int s)
+    // ring slot of row (current step row - back), for phase PH: block pointer + constant
+    template <int PH, int BACK>
+    __device__ __forceinline__ T* rslot() const
     {
-        const bool vrow = (y >= a.row_lo) && (y < a.row_hi);
-        const bool v = vrow && (c < a.pitch);
-        const i64 off = v ? ((i64)y * a.pitch + c) : ((i64)a.row_lo * a.pitch);
-        cp_async16(slot_u(s), a.u_in + off, v);
-        cp_async16(slot_f(s), a.f + off, v);
+        constexpr int rel = PH - BACK;                       // slot index relative to this iteration's block
+        constexpr int b = (rel >= 0) ? rel / 3 : -((-rel + 2) / 3);
+        constexpr int s = rel - 3 * b;
+        return blk[(b + 4) & 3] + s * C::SLOT_ELEMS;
+    }
+    template <int PH, int BACK>
+    __device__ __forceinline__ T* cslot() const
+    {
+        constexpr int rel = PH - BACK;
+        constexpr int b = (rel >= 0) ? rel / 3 : -((-rel + 2) / 3);
+        constexpr int s = rel - 3 * b;
+        return cblk[(b + 4) & 3] + s * C::CSLOT_ELEMS;
+    }
+
+    // prefetch row y into the slot that is REL slots ahead of this iteration's block start
+    template <int REL>
+    __device__ __forceinline__ void issue(int y)
+    {
+        constexpr int b = REL / 3, s = REL % 3;
+        T* dst = blk[b & 3] + s * C::SLOT_ELEMS;
+        const bool v = lane_ld && (y >= a.row_lo) && (y < a.row_hi);
+        cp_async16(dst, v ? g_u : a.u_in + (i64)a.row_lo * a.pitch, v);
+        cp_async16(dst + 32 * V, v ? g_f : a.f + (i64)a.row_lo * a.pitch, v);
+        g_u += a.pitch;
+        g_f += a.pitch;
         if (MODE == MODE_POST) {
             const int ic = (y + 1) >> 1;
-            const int jc = c >> 1;
-            const bool vc = (ic >= a.crow_lo) && (ic < a.crow_hi) && (y >= 0) && (jc < a.pitch_c);
-            const i64 offc = vc ? ((i64)ic * a.pitch_c + jc) : ((i64)a.crow_lo * a.pitch_c);
-            cp_async8(slot_c(s), a.ec + offc, vc);
+            const bool vc = lane_ldc && (ic >= a.crow_lo) && (ic < a.crow_hi) && (y >= 0);
+            const T* src = a.ec + (vc ? ((i64)ic * a.pitch_c + (c >> 1)) : (i64)a.crow_lo * a.pitch_c);
+            cp_async8(cblk[b & 3] + s * C::CSLOT_ELEMS, src, vc);
         }
         cp_async_commit();
     }
-
-    __device__ __forceinline__ bool interior(int y, int x) const { return y >= 1 && y < a.N && x >= 1 && x < a.N; }
 
     template <int NEW>
     __device__ __forceinline__ void put_row(int s, const T (&v)[V])
@@ -137,6 +172,18 @@ struct Streamer {
         WR[s][NEW] = __shfl_down_sync(FULL, v[0], 1);
     }
 
+    // Dirichlet ring: only rows 0 / N (rows beyond them are zero by construction) and, on
+    // strips touching the boundary, the columns flagged in cz[] ever need forcing.
+    __device__ __forceinline__ void mask_row(int row, T (&o)[V]) const
+    {
+        const bool rowbad = (row <= 0) || (row >= a.N);
+        if (rowbad || edge) {
+#pragma unroll
+            for (int k = 0; k < V; ++k)
+                if (rowbad || cz[k]) o[k] = (T)0;
+        }
+    }
+
     // one pipeline step: row y of the input arrives
     template <int PH>
     __device__ __forceinline__ void step(int y)
@@ -144,15 +191,15 @@ struct Streamer {
         constexpr int NEW = PH, MID = (PH + 2) % 3, OLD = (PH + 1) % 3;
         T cur[V];
         // ---- stage 0: the incoming row (POST: plus the interpolated coarse correction) ----
-        ldv<T>(slot_u(slot), cur);
+        ldv<T>(rslot<PH, 0>(), cur);
         if (MODE == MODE_POST) {
             T ca[H + 1], cb[H + 1], e[V];
-            const T* pa = slot_c(slot);
+            const T* pa = cslot<PH, 0>();
 #pragma unroll
             for (int k = 0; k < H; ++k) cb[k] = pa[k];
             cb[H] = __shfl_down_sync(FULL, cb[0], 1);
-            if (y & 1) {
-                const T* pp = slot_c(slot_back(1));
+            if (y & 1) {  // (y parity is warp-uniform, so both branches are convergent)
+                const T* pp = cslot<PH, 1>();
 #pragma unroll
                 for (int k = 0; k < H; ++k) ca[k] = pp[k];
                 ca[H] = __shfl_down_sync(FULL, ca[0], 1);
@@ -161,7 +208,7 @@ struct Streamer {
                     e[2 * k] = (T)0.5 * (ca[k] + cb[k]);                                       // P:407
                     e[2 * k + 1] = (T)0.25 * (((ca[k] + cb[k]) + ca[k + 1]) + cb[k + 1]);      // P:419
                 }
-            } else {  // (y parity is warp-uniform, so both branches are convergent)
+            } else {
 #pragma unroll
                 for (int k = 0; k < H; ++k) {
                     e[2 * k] = cb[k];                                                          // P:401
@@ -169,10 +216,8 @@ struct Streamer {
                 }
             }
 #pragma unroll
-            for (int k = 0; k < V; ++k) {
-                const T val = cur[k] + e[k];                                                   // P:623
-                cur[k] = interior(y, c + k) ? val : (T)0;
-            }
+            for (int k = 0; k < V; ++k) cur[k] = cur[k] + e[k];                                // P:623
+            mask_row(y, cur);
         }
         put_row<NEW>(0, cur);
 
@@ -181,83 +226,103 @@ struct Streamer {
         for (int s = 1; s <= NS; ++s) {
             const int rs = y - s;
             T ff[V], o[V];
-            ldv<T>(slot_f(slot_back(s)), ff);
+            if (s == 1) ldv<T>(rslot<PH, 1>() + 32 * V, ff);
+            else if (s == 2) ldv<T>(rslot<PH, 2>() + 32 * V, ff);
+            else if (s == 3) ldv<T>(rslot<PH, 3>() + 32 * V, ff);
+            else ldv<T>(rslot<PH, 4>() + 32 * V, ff);
 #pragma unroll
             for (int k = 0; k < V; ++k) {
                 const T l = (k == 0) ? WL[s - 1][MID] : W[s - 1][MID][k - 1];
                 const T r = (k == V - 1) ? WR[s - 1][MID] : W[s - 1][MID][k + 1];
                 const T sig = sigma4<T>(W[s - 1][OLD][k], W[s - 1][NEW][k], l, r);
-                T val;
                 if (RBGS) {
                     const int colour = (s - 1) & 1;
-                    val = (((rs + c + k) & 1) == colour) ? gs_pt<T>(ff[k], sig) : W[s - 1][MID][k];
+                    o[k] = (((rs + c + k) & 1) == colour) ? gs_pt<T>(ff[k], sig) : W[s - 1][MID][k];
                 } else {
-                    val = jacobi_pt<T>(a.c0, a.c1, W[s - 1][MID][k], ff[k], sig);
+                    o[k] = jacobi_pt<T>(a.c0, a.c1, W[s - 1][MID][k], ff[k], sig);
                 }
-                o[k] = interior(rs, c + k) ? val : (T)0;
             }
+            mask_row(rs, o);
             if (s < C::NW) put_row<NEW>(s, o);
             if (s == NS) {
-                if (rs >= y0 && rs < y1 && c >= out_lo && c < out_hi && c < a.N)
-                    stv<T>(a.u_out + (i64)rs * a.pitch + c, o);
+                if (lane_st && rs >= y0 && rs < y1) stv<T>(g_o, o);
+                g_o += a.pitch;
             }
         }
 
         // ---- PRE: residual of u_NS (row y-NS-1) and full weighting (coarse row when that row is odd) ----
         if (MODE == MODE_PRE) {
             const int rr = y - NS - 1;
-            T ff[V];
-            ldv<T>(slot_f(slot_back(NS + 1)), ff);
+            T ff[V], o[V];
+            ldv<T>(rslot<PH, NS + 1>() + 32 * V, ff);
 #pragma unroll
             for (int k = 0; k < V; ++k) {
                 const T l = (k == 0) ? WL[NS][MID] : W[NS][MID][k - 1];
                 const T r = (k == V - 1) ? WR[NS][MID] : W[NS][MID][k + 1];
-                const T val = resid_pt<T>(W[NS][MID][k], ff[k], sigma4<T>(W[NS][OLD][k], W[NS][NEW][k], l, r));
-                R[NEW][k] = interior(rr, c + k) ? val : (T)0;
+                o[k] = resid_pt<T>(W[NS][MID][k], ff[k], sigma4<T>(W[NS][OLD][k], W[NS][NEW][k], l, r));
             }
-            RL[NEW] = __shfl_up_sync(FULL, R[NEW][V - 1], 1);
+            mask_row(rr, o);
+#pragma unroll
+            for (int k = 0; k < V; ++k) R[NEW][k] = o[k];
+            RL[NEW] = __shfl_up_sync(FULL, o[V - 1], 1);
             if (rr & 1) {
                 const int yc = rr - 1;  // fine centre row 2I (MID of the residual window)
-                T o[H];
+                T oc[H];
 #pragma unroll
                 for (int j = 0; j < H; ++j) {
                     const int k = 2 * j;
                     const T nw = (k == 0) ? RL[OLD] : R[OLD][k - 1];
                     const T wv = (k == 0) ? RL[MID] : R[MID][k - 1];
                     const T sw = (k == 0) ? RL[NEW] : R[NEW][k - 1];
-                    const T val = fw_pt<T>(a.w, nw, R[OLD][k + 1], sw, R[NEW][k + 1], wv, R[MID][k + 1],
-                                           R[OLD][k], R[NEW][k], R[MID][k]);
-                    const int J = (c + k) >> 1;
-                    o[j] = (J >= 1 && J < a.Nc) ? val : (T)0;
+                    oc[j] = fw_pt<T>(a.w, nw, R[OLD][k + 1], sw, R[NEW][k + 1], wv, R[MID][k + 1],
+                                     R[OLD][k], R[NEW][k], R[MID][k]);
+                    if (edge) {
+                        const int J = (c + k) >> 1;
+                        if (!(J >= 1 && J < a.Nc)) oc[j] = (T)0;
+                    }
                 }
-                if (yc >= y0 && yc < y1 && c >= out_lo && c < out_hi && c < a.N) {
+                if (lane_st && yc >= y0 && yc < y1) {
                     const i64 offc = (i64)(yc >> 1) * a.pitch_c + (c >> 1);
                     if constexpr (H == 1) {
-                        a.fc[offc] = o[0];
+                        a.fc[offc] = oc[0];
                         if (a.uc) a.uc[offc] = (T)0;
                     } else {
-                        *reinterpret_cast<float2*>(a.fc + offc) = make_float2((float)o[0], (float)o[H - 1]);
+                        *reinterpret_cast<float2*>(a.fc + offc) = make_float2((float)oc[0], (float)oc[H - 1]);
                         if (a.uc) *reinterpret_cast<float2*>(a.uc + offc) = make_float2(0.f, 0.f);
                     }
                 }
             }
         }
-        slot = (slot + 1 == C::DEPTH) ? 0 : slot + 1;
     }
 
-    __device__ __forceinline__ void run(T* ring_base, int warp, int lane_, int item)
+    __device__ __forceinline__ void set_blocks(int q)
     {
-        lane = lane_;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            blk[j] = ring + ((q + j) & 3) * BLK;
+            if (MODE == MODE_POST) cblk[j] = cring + ((q + j) & 3) * CBLK;
+        }
+    }
+
+    __device__ __forceinline__ void run(T* ring_base, int warp, int lane, int item)
+    {
         const int chunk = item / a.strips;
         const int strip = item - chunk * a.strips;
         const int X0 = strip * C::OUTW;
         c = X0 + V * lane;
-        out_lo = (strip == 0) ? 0 : X0 + V * C::HLANES;
-        out_hi = X0 + V * C::HLANES + C::OUTW;
+        const int out_lo = (strip == 0) ? 0 : X0 + V * C::HLANES;
+        const int out_hi = X0 + V * C::HLANES + C::OUTW;
         y0 = a.ya + chunk * a.ry;
         y1 = min(y0 + a.ry, a.yb);
-        ring = ring_base + (size_t)warp * C::DEPTH * C::SLOT_ELEMS + lane * V;
+        ring = ring_base + (size_t)warp * C::WARP_ELEMS + lane * V;
+        cring = ring_base + (size_t)warp * C::WARP_ELEMS + C::DEPTH * C::SLOT_ELEMS + lane * H;
         const int ylo = y0 - C::HT, yhi = y1 - 1 + C::HB;
+        lane_ld = (c < a.pitch);
+        lane_ldc = ((c >> 1) < a.pitch_c);
+        lane_st = (c >= out_lo) && (c < out_hi) && (c < a.N);
+        edge = (strip == 0) || (X0 + 32 * V >= a.N);
+#pragma unroll
+        for (int k = 0; k < V; ++k) cz[k] = (c + k < 1) || (c + k >= a.N);
 
 #pragma unroll
         for (int s = 0; s < (C::NW > 0 ? C::NW : 1); ++s)
@@ -275,31 +340,42 @@ struct Streamer {
             RL[p] = (T)0;
         }
 
-        // prologue: D rows in flight
-#pragma unroll
-        for (int i = 0; i < C::D; ++i) issue(ylo + i, i);
-        slot = 0;
-        int pf = C::D;  // ring slot the next prefetch goes to
+        g_u = a.u_in + (i64)ylo * a.pitch + c;
+        g_f = a.f + (i64)ylo * a.pitch + c;
+        g_o = a.u_out + (i64)(ylo - NS) * a.pitch + c;   // row produced by stage NS in the first step
+
+        // prologue: rows ylo .. ylo+D-1 into slots 0 .. D-1
+        set_blocks(0);
+        issue_prologue<0>(ylo);
+        int q = 0;
         for (int y = ylo; y <= yhi; y += 3) {
-            issue(y + C::D, pf);
-            pf = (pf + 1 == C::DEPTH) ? 0 : pf + 1;
+            set_blocks(q);
+            issue<C::D>(y + C::D);
             cp_async_wait<C::D>();
             step<0>(y);
-            issue(y + 1 + C::D, pf);
-            pf = (pf + 1 == C::DEPTH) ? 0 : pf + 1;
+            issue<C::D + 1>(y + 1 + C::D);
             cp_async_wait<C::D>();
             step<1>(y + 1);
-            issue(y + 2 + C::D, pf);
-            pf = (pf + 1 == C::DEPTH) ? 0 : pf + 1;
+            issue<C::D + 2>(y + 2 + C::D);
             cp_async_wait<C::D>();
             step<2>(y + 2);
+            q = (q + 1) & 3;
         }
         cp_async_wait<0>();
+    }
+
+    template <int I>
+    __device__ __forceinline__ void issue_prologue(int ylo)
+    {
+        if constexpr (I < C::D) {
+            issue<I>(ylo + I);
+            issue_prologue<I + 1>(ylo);
+        }
     }
 };
 
 template <typename T, int NS, int MODE, bool RBGS>
-__global__ void __launch_bounds__(kStreamWarps * 32)
+__global__ void __launch_bounds__(kStreamWarps * 32, 16 / kStreamWarps)
 k_stream(const StreamArgs<T> a)
 {
     extern __shared__ __align__(16) unsigned char stream_smem[];

@@ -41,35 +41,59 @@ k_tail(const TailArgs<T> a)
 {
     extern __shared__ __align__(16) unsigned char tail_smem[];
     T* base = reinterpret_cast<T*>(tail_smem);
-    // per-level smem arrays (node grid incl. zero ring, pitch N+1): A = current u, B = scratch, F = rhs
+    // per-level smem arrays (node grid incl. zero ring, pitch N+1): A = current u, B = scratch, F = rhs.
+    // Kept as individually named registers through full unrolling over the (at most 6) levels.
     T* A[kTailMaxLevel + 1];
     T* B[kTailMaxLevel + 1];
     T* F[kTailMaxLevel + 1];
     int visits[kTailMaxLevel + 1];
-    {
-        size_t off = 0;
-        for (int l = a.coarsest; l <= a.top; ++l) {
-            const size_t sz = (size_t)((1 << l) + 1) * ((1 << l) + 1);
-            A[l] = base + off; off += sz;
-            B[l] = base + off; off += sz;
-            F[l] = base + off; off += sz;
-            visits[l] = 0;
-        }
-        for (size_t i = threadIdx.x; i < off; i += kTailThreads) base[i] = (T)0;
+    size_t total = 0;
+#pragma unroll
+    for (int l = 1; l <= kTailMaxLevel; ++l) {
+        const size_t sz = (size_t)((1 << l) + 1) * ((1 << l) + 1);
+        const bool on = (l >= a.coarsest) && (l <= a.top);
+        A[l] = base + total;
+        B[l] = base + total + sz;
+        F[l] = base + total + 2 * sz;
+        if (on) total += 3 * sz;
+        visits[l] = 0;
     }
+    A[0] = B[0] = F[0] = base;
+    visits[0] = 0;
+    for (size_t i = threadIdx.x; i < total; i += kTailThreads) base[i] = (T)0;
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NWARP = kTailThreads / 32;
 
-    // load level `top`
+    // load level `top` (batched: all global loads of a thread are in flight before the first smem store)
     {
         const int N = 1 << a.top, P = N + 1;
-        for (int y = 1 + warp; y < N; y += NWARP)
-            for (int x = 1 + lane; x < N; x += 32) {
-                A[a.top][y * P + x] = a.u[(i64)y * a.pitch + x];
-                F[a.top][y * P + x] = a.f[(i64)y * a.pitch + x];
+        constexpr int MAXIT = ((1 << kTailMaxLevel) + NWARP - 1) / NWARP;
+        T tu[MAXIT][2], tf[MAXIT][2];
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) {
+            const int y = 1 + warp + it * NWARP;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int x = 1 + lane + 32 * h;
+                const bool ok = (y < N) && (x < N);
+                tu[it][h] = ok ? a.u[(i64)y * a.pitch + x] : (T)0;
+                tf[it][h] = ok ? a.f[(i64)y * a.pitch + x] : (T)0;
             }
+        }
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) {
+            const int y = 1 + warp + it * NWARP;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int x = 1 + lane + 32 * h;
+                if ((y < N) && (x < N)) {
+                    A[a.top][y * P + x] = tu[it][h];
+                    F[a.top][y * P + x] = tf[it][h];
+                }
+            }
+        }
     }
     __syncthreads();
 
