@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "comm.cuh"
@@ -109,7 +110,11 @@ Ctx::Ctx(const mg_config& c) : cfg(c)
         MG_CK(cudaMalloc(&d_norm, sizeof(double) * 8));
         MG_CK(cudaMallocHost(&h_norm, sizeof(double) * 8));
     }
-    if (cfg.world > 1) comm = comm_create(*this);
+    if (cfg.world > 1) {
+        comm = comm_create(*this);
+        const char* e = getenv("MGB200_GRAPH_DIST");
+        graph_dist = e && e[0] == '1';
+    }
     fused_setup(*this);
     MG_CK(cudaStreamSynchronize(stream));
 }
@@ -272,7 +277,7 @@ void Ctx::restrict_t(int fine_level, bool from_rhs)
     Level& lcv = L(fine_level - 1);
     const T w = (T)cfg.restrict_weight;
     const T* src = (const T*)(from_rhs ? lf.f : lf.r);
-    if (lf.distributed && !from_rhs) comm_halo_exchange(*this, lf, lf.r, 1);  // r of the neighbour's edge row
+    if (lf.distributed) comm_halo_exchange(*this, lf, (char*)src, 1);  // edge row of the neighbour's r (or f)
     if (lf.distributed && !lcv.distributed) {
         // agglomeration: every rank restricts its slab of coarse rows, then all-gathers
         int lo, hi;
@@ -347,7 +352,7 @@ void Ctx::cycle(int level, int nu1, int nu2, int gamma)
 {
     L(level);
     MG_REQUIRE(nu1 >= 0 && nu2 >= 0 && gamma >= 1, "nu1, nu2 >= 0 and gamma >= 1 required");
-    if (!(cfg.flags & MG_GRAPH) || capturing) {
+    if (!(cfg.flags & MG_GRAPH) || capturing || (cfg.world > 1 && !graph_dist)) {
         cycle_rec(level, nu1, nu2, gamma);
         return;
     }

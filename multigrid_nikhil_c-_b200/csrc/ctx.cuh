@@ -79,6 +79,7 @@ struct Ctx {
     std::map<std::tuple<int, int, int, int, unsigned long long>, GraphEntry> graphs;
     Comm* comm = nullptr;
     int aggl_level = 0;  // levels <= aggl_level are replicated on every rank
+    bool graph_dist = false;  // capture NCCL exchanges into cycle graphs (MGB200_GRAPH_DIST=1)
 
     explicit Ctx(const mg_config& c);
     ~Ctx();

@@ -128,6 +128,13 @@ class Oracle:
         self._f("mgo_rbgs", out)(_ptr(out), _ptr(fh), _side(out), int(mu), int(nthreads))
         return out
 
+    def rbgs_half(self, v, fh, colour, nthreads=1):
+        """One colour (0 red, 1 black) of one RB-GS sweep."""
+        out = np.array(v, copy=True)
+        self._chk(out, fh)
+        self._f("mgo_rbgs_half", out)(_ptr(out), _ptr(fh), _side(out), int(colour), int(nthreads))
+        return out
+
     def residual(self, v, fh, nthreads=1):
         """P:589-608."""
         self._chk(v, fh)

@@ -48,6 +48,7 @@ int mgo_max_threads(void);
     void mgo_jacobi_constants##S(double omega, T* c0, T* c1);                                        \
     void mgo_jacobirelaxation##S(T* v, const T* fh, int n, int mu, double omega, int nthreads);      \
     void mgo_rbgs##S(T* v, const T* fh, int n, int mu, int nthreads);                                \
+    void mgo_rbgs_half##S(T* v, const T* fh, int n, int colour, int nthreads);                       \
     void mgo_residual##S(const T* v, const T* fh, T* r, int n, int nthreads);                        \
     double mgo_sumsq##S(const T* r, int n);                                                          \
     void mgo_restriction2d##S(const T* vec_h, int nh, T* vec_2h, double w, int nthreads);            \

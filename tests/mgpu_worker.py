@@ -1,0 +1,85 @@
+"""Multi-GPU parity worker: run under torchrun (one rank per GPU).  Every rank checks the
+rows it owns against the single-domain CPU oracle, bit for bit (results must not depend on
+the decomposition).  Exit code != 0 on any mismatch."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import mgb200  # noqa: E402
+import oracle  # noqa: E402
+from conftest import rand_vec  # noqa: E402
+
+pkg = mgb200.package
+mgdist = __import__("importlib").import_module("multigrid_nikhil_c-_b200.dist")
+
+
+def check(mg, level, got, want, what):
+    a = mgdist.owned_slice(mg, level, got)
+    b = mgdist.owned_slice(mg, level, want)
+    if not np.array_equal(a, b):
+        d = np.abs(a - b)
+        raise AssertionError(f"rank {mg.rank}: {what}: max diff {d.max():.3e}, {int((a != b).sum())} mismatches")
+
+
+def main():
+    rank, world, local = mgdist.env_ranks()
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    o = oracle.get()
+    n_checks = 0
+    for dtype in (np.float64, np.float32):
+        for level, aggl in ((7, 4), (8, 6), (9, 5)):
+            if (1 << (aggl + 1)) // world < 8:
+                continue
+            x, b = rand_vec(level, dtype, 41), rand_vec(level, dtype, 42, 1e-3)
+            for smoother, sid in (("jacobi", 0), ("rbgs", 1)):
+                mg = mgdist.create(level, dtype=dtype, smoother=smoother, agglomerate_level=aggl)
+                assert mg.info(mgb200.capi.MG_INFO_DISTRIBUTED, level) == 1
+                assert mg.info(mgb200.capi.MG_INFO_DISTRIBUTED, aggl) == 0
+                # smoother
+                mg.set_u(level, x); mg.set_rhs(level, b); mg.smooth(level, 3)
+                want = o.jacobirelaxation(x, b, 3) if sid == 0 else o.rbgs(x, b, 3)
+                check(mg, level, mg.get_u(level), want, f"smooth {smoother} L{level} {dtype.__name__}")
+                # residual + norm (identical on every rank)
+                mg.set_u(level, x)
+                nrm = mg.residual(level, norm=True)
+                r = o.residual(x, b)
+                check(mg, level, mg.get_r(level), r, "residual")
+                assert abs(nrm - o.norm2(r)) <= 1e-12 * o.norm2(r)
+                t = torch.tensor([nrm], dtype=torch.float64, device="cuda")
+                lst = [torch.zeros_like(t) for _ in range(world)]
+                dist.all_gather(lst, t)
+                assert all(float(v.item()) == nrm for v in lst), "norm differs between ranks"
+                # cycles: V, W; FMG; solve
+                for gamma in (1, 2):
+                    p = oracle.Params(smoother=sid, gamma=gamma, nthreads=2)
+                    mg.set_u(level, x); mg.set_rhs(level, b)
+                    want = x
+                    for k in range(2):
+                        mg.cycle(level, 2, 2, gamma)
+                        want = o.vcyclemultigrid(want, b, p)
+                        check(mg, level, mg.get_u(level), want, f"cycle {k} gamma={gamma} {smoother} L{level} aggl{aggl}")
+                        n_checks += 1
+                p = oracle.Params(smoother=sid, nthreads=2)
+                check(mg, level, mg.fullmultigrid(b, 1, 2, 2), o.fullmultigrid(b, 1, p), "fmg")
+                mg.set_rhs(level, b); mg.zero_u(level)
+                k, rel, hist = mg.solve(1e-8, 30)
+                u, ko, ho = o.solve(np.zeros_like(b), b, 1e-8, 30, p)
+                assert k == ko, (k, ko)
+                assert np.allclose(hist, ho, rtol=1e-10, atol=0)
+                check(mg, level, mg.get_u(level), u, "solve")
+                mg.close()
+    dist.barrier()
+    if rank == 0:
+        print(f"MGPU OK world={world} checks={n_checks}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,26 @@
+"""Row-slab multi-GPU parity: results on 2/4/8 GPUs are bit-identical to the
+oracle (hence to the single-GPU run) for any agglomeration level.  Needs >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slabs_match_oracle(world):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 29500 + world
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "MGPU OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
