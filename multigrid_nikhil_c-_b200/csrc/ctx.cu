@@ -69,7 +69,7 @@ Ctx::Ctx(const mg_config& c) : cfg(c)
     }
 
     levels.resize(cfg.finest_level + 1);
-    const int halo = 1;
+    const int halo = kHaloRows;
     for (int l = cfg.coarsest_level; l <= cfg.finest_level; ++l) {
         Level& lv = levels[l];
         lv.level = l;
@@ -145,6 +145,22 @@ const Level& Ctx::L(int level) const { return const_cast<Ctx*>(this)->L(level); 
 
 void Ctx::sync() { MG_CK(cudaStreamSynchronize(stream)); }
 
+static int& halo_ref(Level& lv, Ctx::Which w) { return w == Ctx::W_U ? lv.hv_u : (w == Ctx::W_F ? lv.hv_f : lv.hv_r); }
+
+void Ctx::set_halo(Level& lv, Which w, int depth) { halo_ref(lv, w) = depth; }
+
+// lazy halo exchange: make `depth` halo rows of the array valid (no-op on replicated levels)
+void Ctx::ensure_halo(Level& lv, Which w, int depth)
+{
+    if (!lv.distributed || depth <= 0) return;
+    MG_REQUIRE(depth <= kHaloRows, "halo depth exceeds the stored halo");
+    int& hv = halo_ref(lv, w);
+    if (hv >= depth) return;
+    char* base = (w == W_U) ? lv.u[lv.cur] : (w == W_F ? lv.f : lv.r);
+    comm_halo_exchange(*this, lv, base, depth);
+    hv = depth;
+}
+
 unsigned long long Ctx::parity_mask() const
 {
     unsigned long long m = 0;
@@ -182,6 +198,7 @@ void Ctx::set_host(int level, Which w, const void* host)
     MG_CK(cudaMemcpy2DAsync(dst, (size_t)lv.pitch * esize, src, (size_t)n * esize, (size_t)n * esize,
                             (size_t)(yb - ya), cudaMemcpyHostToDevice, stream));
     MG_CK(cudaStreamSynchronize(stream));
+    set_halo(lv, w, kHaloRows);
 }
 
 void Ctx::get_host(int level, Which w, void* host)
@@ -201,6 +218,7 @@ void Ctx::zero_u(int level)
 {
     Level& lv = L(level);
     MG_CK(cudaMemsetAsync(lv.alloc[lv.cur], 0, lv.bytes, stream));
+    lv.hv_u = kHaloRows;
 }
 
 void Ctx::force_constant(double fval)
@@ -212,6 +230,7 @@ void Ctx::force_constant(double fval)
     if (f64()) launch_fill<double>(stream, lc, (double*)lv.f, lv.pitch, lv.N, ya, yb, b);
     else launch_fill<float>(stream, lc, (float*)lv.f, lv.pitch, lv.N, ya, yb, (float)b);
     MG_CK(cudaGetLastError());
+    lv.hv_f = kHaloRows;
 }
 
 // ---------------------------------------------------------------------------------
@@ -231,18 +250,20 @@ void Ctx::smooth_t(int level, int nu)
         while (s < nu) {
             const int did = fused_jacobi<T>(*this, lv, nu - s, c0, c1);  // temporally blocked sweeps (0 if n/a)
             if (did > 0) { s += did; continue; }
+            ensure_halo(lv, W_U, 1);
             launch_jacobi<T>(stream, lc, (const T*)lv.u[lv.cur], (T*)lv.u[lv.cur ^ 1], (const T*)lv.f,
                              lv.pitch, lv.N, lv.own_lo, lv.own_hi, c0, c1);
             lv.cur ^= 1;
-            if (lv.distributed) comm_halo_exchange(*this, lv, lv.u[lv.cur], 1);
+            lv.hv_u = 0;
             ++s;
         }
     } else {
         for (int s = 0; s < nu; ++s)
             for (int colour = 0; colour < 2; ++colour) {
+                ensure_halo(lv, W_U, 1);
                 launch_rbgs<T>(stream, lc, (T*)lv.u[lv.cur], (const T*)lv.f, lv.pitch, lv.N, lv.own_lo,
                                lv.own_hi, colour);
-                if (lv.distributed) comm_halo_exchange(*this, lv, lv.u[lv.cur], 1);
+                lv.hv_u = 0;
             }
     }
     MG_CK(cudaGetLastError());
@@ -252,6 +273,8 @@ template <typename T>
 double Ctx::residual_t(int level, bool want_norm, bool store)
 {
     Level& lv = L(level);
+    ensure_halo(lv, W_U, 1);
+    if (store) lv.hv_r = 0;
     const int np = launch_residual<T>(stream, lc, (const T*)lv.u[lv.cur], (const T*)lv.f, (T*)lv.r, lv.pitch,
                                       lv.N, lv.own_lo, lv.own_hi, want_norm ? d_partials : nullptr, store);
     MG_CK(cudaGetLastError());
@@ -277,26 +300,25 @@ void Ctx::restrict_t(int fine_level, bool from_rhs)
     Level& lcv = L(fine_level - 1);
     const T w = (T)cfg.restrict_weight;
     const T* src = (const T*)(from_rhs ? lf.f : lf.r);
-    if (lf.distributed) comm_halo_exchange(*this, lf, (char*)src, 1);  // edge row of the neighbour's r (or f)
+    ensure_halo(lf, from_rhs ? W_F : W_R, 1);   // edge row of the neighbour's r (or f)
+    if (!from_rhs) lcv.cur = 0;                  // fixed buffer for the zero guess keeps graph replays valid
     if (lf.distributed && !lcv.distributed) {
         // agglomeration: every rank restricts its slab of coarse rows, then all-gathers
         int lo, hi;
         slab_rows(lcv.level, cfg.rank, cfg.world, &lo, &hi);
-        if (!from_rhs) { lcv.cur = 0; }
-        launch_restrict<T>(stream, lc, src, lf.pitch, (T*)lcv.f, from_rhs ? nullptr : (T*)lcv.u[lcv.cur],
-                           lcv.pitch, lcv.N, lo, hi, w);
+        launch_restrict<T>(stream, lc, src, lf.pitch, (T*)lcv.f, (T*)nullptr, lcv.pitch, lcv.N, lo, hi, w);
         MG_CK(cudaGetLastError());
         comm_allgather_rows(*this, lcv, lcv.f);
         if (!from_rhs) MG_CK(cudaMemsetAsync(lcv.alloc[lcv.cur], 0, lcv.bytes, stream));
         return;
     }
-    if (!from_rhs) lcv.cur = 0;  // fixed buffer for the zero guess keeps graph replays valid
     launch_restrict<T>(stream, lc, src, lf.pitch, (T*)lcv.f, from_rhs ? nullptr : (T*)lcv.u[lcv.cur], lcv.pitch,
                        lcv.N, lcv.own_lo, lcv.own_hi, w);
     MG_CK(cudaGetLastError());
+    lcv.hv_f = 0;
     if (lcv.distributed && !from_rhs) {
-        // halo rows of the zero guess: clear them too
-        comm_zero_halo(*this, lcv, lcv.u[lcv.cur]);
+        comm_zero_halo(*this, lcv, lcv.u[lcv.cur]);   // halo rows of the zero guess
+        lcv.hv_u = kHaloRows;
     }
 }
 
@@ -305,12 +327,12 @@ void Ctx::prolong_t(int fine_level, bool add)
 {
     Level& lf = L(fine_level);
     Level& lcv = L(fine_level - 1);
-    // coarse halos are valid after every smoothing sweep; every stored interior fine row
-    // (owned + halo) can therefore be prolonged locally, no exchange needed afterwards.
-    const int ya = std::max(lf.st_lo, 1), yb = std::min(lf.st_hi, lf.N);
-    launch_prolong<T>(stream, lc, (const T*)lcv.u[lcv.cur], lcv.pitch, (T*)lf.u[lf.cur], lf.pitch, lf.N, ya, yb,
-                      add);
+    // the last owned fine row (odd) interpolates from the first coarse halo row
+    ensure_halo(lcv, W_U, 1);
+    launch_prolong<T>(stream, lc, (const T*)lcv.u[lcv.cur], lcv.pitch, (T*)lf.u[lf.cur], lf.pitch, lf.N, lf.own_lo,
+                      lf.own_hi, add);
     MG_CK(cudaGetLastError());
+    lf.hv_u = 0;
 }
 
 void Ctx::smooth(int level, int nu) { f64() ? smooth_t<double>(level, nu) : smooth_t<float>(level, nu); }

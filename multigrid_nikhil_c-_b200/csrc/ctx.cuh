@@ -40,6 +40,8 @@ struct MgError : std::runtime_error {
 
 struct Comm;  // comm.cuh (row-slab halo exchange; null when world == 1)
 
+constexpr int kHaloRows = 6;  // halo rows stored per side on distributed levels (deepest fused kernel: RB-GS PRE, NS=4)
+
 struct Level {
     int level = 0;
     int N = 0;            // node index range 0..N, N = 2^level
@@ -53,6 +55,9 @@ struct Level {
     char* f = nullptr;
     char* r = nullptr;
     int cur = 0;                 // which of u[] holds the current iterate
+    // number of valid halo rows (distributed levels) of the current u, of f and of r;
+    // an operator that rewrites only the owned rows sets it to 0, Ctx::ensure_halo exchanges lazily
+    int hv_u = 0, hv_f = 0, hv_r = 0;
 };
 
 struct GraphEntry {
@@ -109,6 +114,8 @@ struct Ctx {
     float time_op(int op, int level, int reps);
 
     void sync();
+    void ensure_halo(Level& lv, Which w, int depth);
+    void set_halo(Level& lv, Which w, int depth);
     unsigned long long parity_mask() const;
     void set_parity(unsigned long long m);
 

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 
+#include "comm.cuh"
 #include "stream.cuh"
 #include "tail.cuh"
 
@@ -87,13 +88,17 @@ static void launch_stream(Ctx& ctx, Level& lv, Level* lcv)
     a.pitch_c = 0;
     a.Nc = 0;
     a.crow_lo = a.crow_hi = 0;
+    // lazy halo exchanges (no-ops on replicated levels): rows the stencil pipeline reaches into
+    ctx.ensure_halo(lv, Ctx::W_U, C::HT - (MODE == MODE_POST ? 1 : 0));
+    ctx.ensure_halo(lv, Ctx::W_F, NS + (MODE == MODE_PRE ? 1 : 0) - (MODE == MODE_SWEEPS ? 1 : 0));
     if (MODE == MODE_PRE) {
         lcv->cur = 0;
         a.fc = (T*)lcv->f;
-        a.uc = (T*)lcv->u[0];
+        a.uc = (lv.distributed && !lcv->distributed) ? nullptr : (T*)lcv->u[0];
         a.pitch_c = lcv->pitch;
         a.Nc = lcv->N;
     } else if (MODE == MODE_POST) {
+        ctx.ensure_halo(*lcv, Ctx::W_U, NS / 2 + 1);
         a.ec = (const T*)lcv->u[lcv->cur];
         a.pitch_c = lcv->pitch;
         a.Nc = lcv->N;
@@ -106,11 +111,23 @@ static void launch_stream(Ctx& ctx, Level& lv, Level* lcv)
     ++ctx.lc.n;
     MG_CK(cudaGetLastError());
     lv.cur ^= 1;
+    lv.hv_u = 0;
+    if (MODE == MODE_PRE) {
+        if (lv.distributed && !lcv->distributed) {
+            // agglomeration: gather the coarse right-hand side everywhere, zero guess on the full grid
+            comm_allgather_rows(ctx, *lcv, lcv->f);
+            MG_CK(cudaMemsetAsync(lcv->alloc[0], 0, lcv->bytes, ctx.stream));
+        } else if (lcv->distributed) {
+            lcv->hv_f = 0;
+            comm_zero_halo(ctx, *lcv, lcv->u[0]);
+            lcv->hv_u = kHaloRows;
+        }
+    }
 }
 
-static bool stream_ok(const Ctx& ctx, const Level& lv)
+static bool stream_ok(const Ctx& ctx, const Level&)
 {
-    return (ctx.cfg.flags & MG_FUSED) && !lv.distributed;
+    return (ctx.cfg.flags & MG_FUSED) != 0;
 }
 
 // temporally blocked sweeps: returns the number of sweeps performed (0 = not applicable)
@@ -213,7 +230,7 @@ bool fused_cycle_level(Ctx& ctx, int level, int nu1, int nu2, int gamma)
     if (level <= ctx.cfg.coarsest_level) return false;
     Level& lv = ctx.L(level);
     Level& lcv = ctx.L(level - 1);
-    if (!stream_ok(ctx, lv) || lcv.distributed != lv.distributed) return false;
+    if (!stream_ok(ctx, lv)) return false;
     if (nu1 < 1 || nu2 < 1) return false;
     if (ctx.f64()) pre_fused<double>(ctx, lv, lcv, nu1);
     else pre_fused<float>(ctx, lv, lcv, nu1);
@@ -229,7 +246,7 @@ bool fused_time_hook(Ctx& ctx, int level, bool pre)
     if (level <= ctx.cfg.coarsest_level) return false;
     Level& lv = ctx.L(level);
     Level& lcv = ctx.L(level - 1);
-    if (!stream_ok(ctx, lv) || lcv.distributed) return false;
+    if (!stream_ok(ctx, lv)) return false;
     if (pre) {
         if (ctx.f64()) pre_fused<double>(ctx, lv, lcv, 2);
         else pre_fused<float>(ctx, lv, lcv, 2);

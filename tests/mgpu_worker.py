@@ -33,13 +33,16 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     o = oracle.get()
     n_checks = 0
-    for dtype in (np.float64, np.float32):
-        for level, aggl in ((7, 4), (8, 6), (9, 5)):
+    cases = [(np.float64, 7, 4, "jacobi", True), (np.float64, 7, 4, "rbgs", True), (np.float64, 9, 6, "jacobi", True),
+             (np.float64, 9, 5, "rbgs", True), (np.float64, 8, 5, "jacobi", False), (np.float64, 8, 6, "rbgs", False),
+             (np.float32, 8, 6, "jacobi", True), (np.float32, 8, 5, "rbgs", True), (np.float64, 10, 7, "jacobi", True)]
+    for dtype, level, aggl, smoother, fused in cases:
             if (1 << (aggl + 1)) // world < 8:
                 continue
             x, b = rand_vec(level, dtype, 41), rand_vec(level, dtype, 42, 1e-3)
-            for smoother, sid in (("jacobi", 0), ("rbgs", 1)):
-                mg = mgdist.create(level, dtype=dtype, smoother=smoother, agglomerate_level=aggl)
+            sid = 0 if smoother == "jacobi" else 1
+            if True:
+                mg = mgdist.create(level, dtype=dtype, smoother=smoother, agglomerate_level=aggl, fused=fused)
                 assert mg.info(mgb200.capi.MG_INFO_DISTRIBUTED, level) == 1
                 assert mg.info(mgb200.capi.MG_INFO_DISTRIBUTED, aggl) == 0
                 # smoother
