@@ -200,6 +200,7 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     comm = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the single JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         blob = [mgb200.comm_id() if rank == 0 else None]
