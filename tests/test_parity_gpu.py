@@ -219,3 +219,22 @@ def test_errors_are_loud(mgb):
             mg.set_u(5, np.zeros(10))
     with pytest.raises(mgb.capi.MgError):
         mgb.Multigrid(3, coarsest_level=4)
+
+
+def test_cpp_driver_example_runs_like_the_reference_main(mgb, tmp_path):
+    """include/mgb200_driver.hpp: the reference's function names over the C ABI
+    (examples/poisson_main.cpp == main() P:658-731).  257^2, V(2,2): 13 cycles (C.3)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "multigrid_nikhil_c-_b200", "lib")
+    exe = str(tmp_path / "poisson_main")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "examples", "poisson_main.cpp"), "-o", exe, "-L" + libdir, "-lmgb200",
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe, "8", "1", "2"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "Size of finest level solution is 65025" in out.stdout
+    assert "V(2,2) solve: 13 cycles" in out.stdout and "Program Running Correctly" in out.stdout
+    # FMG with one V(2,2) per level (mu0 = 0): the discrete solution is within 2% in the max norm
+    umax = float(out.stdout.split("max u = ")[1].split()[0])
+    assert abs(umax - 0.2946818) < 0.01
