@@ -1,0 +1,132 @@
+// oracle/ref_shim.cpp — TEST INFRASTRUCTURE.  Compiles the reference's own translation unit
+// (included from where it lies under /root/reference, never copied) against the stub
+// SYCL/oneMKL headers in oracle/stub/, and exposes a few of its functions through a C ABI
+// so that tests can pin the oracle against the REAL reference code:
+//   interpolation2d (P:337), restriction2d (P:531, as written: integer weight 0),
+//   globalforcefunction (P:283), the level setup of main() (P:661-690) + coo_to_csr (P:55),
+//   jacobirelaxation / vcyclemultigrid / fullmultigrid as written (call structure, E1-E4).
+#include <cstring>
+
+#define main ref_main
+#include REF_SOURCE
+#undef main
+
+static cl::sycl::queue g_q;
+static bool g_levels_built = false;
+
+// the body of main()'s level loop P:661-690, executed once (the reference's globals hold the result)
+static void build_levels()
+{
+    if (g_levels_built) return;
+    for (int level = coarsest_level; level <= finest_level; level++) {
+        std::int32_t nodes_per_dim = std::pow(2, level) + 1;
+        std::int32_t original_mat_size = nodes_per_dim * nodes_per_dim;
+        std::int32_t non_bdry_mat_size = (nodes_per_dim - 2) * (nodes_per_dim - 2);
+        int index = level - coarsest_level;
+        std::vector<std::int32_t> rows_lu, cols_lu, rows_d, cols_d;
+        std::vector<float> vals_lu, vals_d;
+        globalstiffenssmatrix(original_mat_size, rows_lu, cols_lu, vals_lu, rows_d, cols_d, vals_d);
+        global_matrices_csr_data_lu[index] = coo_to_csr(non_bdry_mat_size, non_bdry_mat_size, rows_lu.size(), rows_lu, cols_lu, vals_lu);
+        global_matrices_csr_data_d[index] = coo_to_csr(non_bdry_mat_size, non_bdry_mat_size, rows_d.size(), rows_d, cols_d, vals_d);
+        init_matrix_handle(&(jacobi_matrices[index].a_lu_handle));
+        init_matrix_handle(&(jacobi_matrices[index].a_d_handle));
+        set_csr_data(jacobi_matrices[index].a_lu_handle, non_bdry_mat_size, non_bdry_mat_size, oneapi::mkl::index_base::zero,
+                     global_matrices_csr_data_lu[index].indptr.data(), global_matrices_csr_data_lu[index].indices.data(),
+                     global_matrices_csr_data_lu[index].data.data());
+        set_csr_data(jacobi_matrices[index].a_d_handle, non_bdry_mat_size, non_bdry_mat_size, oneapi::mkl::index_base::zero,
+                     global_matrices_csr_data_d[index].indptr.data(), global_matrices_csr_data_d[index].indices.data(),
+                     global_matrices_csr_data_d[index].data.data());
+        jacobi_matrices[index].size = non_bdry_mat_size;
+    }
+    g_levels_built = true;
+}
+
+extern "C" {
+
+int ref_finest_level() { return finest_level; }
+int ref_coarsest_level() { return coarsest_level; }
+void ref_params(int* out3) { out3[0] = mu0; out3[1] = mu1; out3[2] = mu2; }
+
+void ref_counters(long long* out5)
+{
+    out5[0] = refstub::C().gemv; out5[1] = refstub::C().scal; out5[2] = refstub::C().add; out5[3] = refstub::C().sub;
+    out5[4] = refstub::C().gemv_rows;
+}
+void ref_counters_reset() { refstub::C() = refstub::counters(); }
+
+void ref_interpolation2d(const float* in, int m, float* out)
+{
+    std::vector<float> v(in, in + (size_t)m * m);
+    std::vector<float> r = interpolation2d(v);
+    std::memcpy(out, r.data(), r.size() * sizeof(float));
+}
+
+void ref_restriction2d(const float* in, int nh, float* out)
+{
+    std::vector<float> v(in, in + (size_t)nh * nh);
+    std::vector<float> r = restriction2d(v);
+    std::memcpy(out, r.data(), r.size() * sizeof(float));
+}
+
+long long ref_globalforcefunction(float* out_or_null)
+{
+    std::vector<float> r = globalforcefunction();
+    if (out_or_null) std::memcpy(out_or_null, r.data(), r.size() * sizeof(float));
+    return (long long)r.size();
+}
+
+// COO assembly + coo_to_csr for an arbitrary level (what main() does per level, P:662-678).
+// which: 0 = lu part, 1 = diagonal part.  Returns nnz; fills value min/max/sum and the row count.
+long long ref_level_csr_stats(int level, int which, double* out_min_max_sum, int* out_rows, int* out_max_row_nnz)
+{
+    std::int32_t nodes_per_dim = std::pow(2, level) + 1;
+    std::int32_t original_mat_size = nodes_per_dim * nodes_per_dim;
+    std::int32_t n = (nodes_per_dim - 2) * (nodes_per_dim - 2);
+    std::vector<std::int32_t> rows_lu, cols_lu, rows_d, cols_d;
+    std::vector<float> vals_lu, vals_d;
+    globalstiffenssmatrix(original_mat_size, rows_lu, cols_lu, vals_lu, rows_d, cols_d, vals_d);
+    // exact COO sums per (row, col) would be -4 / +1 (sign E3); report the raw COO sum too
+    double coo_sum = 0;
+    for (float v : (which == 0 ? vals_lu : vals_d)) coo_sum += v;
+    csr_data c = which == 0 ? coo_to_csr(n, n, rows_lu.size(), rows_lu, cols_lu, vals_lu)
+                            : coo_to_csr(n, n, rows_d.size(), rows_d, cols_d, vals_d);
+    double mn = 1e300, mx = -1e300, sum = 0;
+    for (float v : c.data) { mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += v; }
+    out_min_max_sum[0] = mn; out_min_max_sum[1] = mx; out_min_max_sum[2] = sum; out_min_max_sum[3] = coo_sum;
+    *out_rows = (int)c.indptr.size() - 1;
+    int mr = 0;
+    for (size_t r = 0; r + 1 < c.indptr.size(); ++r) mr = std::max(mr, c.indptr[r + 1] - c.indptr[r]);
+    *out_max_row_nnz = mr;
+    return (long long)c.data.size();
+}
+
+// one vcyclemultigrid (P:575) at reference level `level` (coarsest_level..finest_level), as written
+void ref_vcyclemultigrid(int level, float* vec_inout, const float* f)
+{
+    build_levels();
+    matrix_elements_for_jacobi a_h = jacobi_matrices[level - coarsest_level];
+    std::vector<float> v(vec_inout, vec_inout + a_h.size), fh(f, f + a_h.size);
+    std::vector<float> r = vcyclemultigrid(g_q, a_h, v, fh);
+    std::memcpy(vec_inout, r.data(), r.size() * sizeof(float));
+}
+
+void ref_jacobirelaxation(int level, float* v_inout, const float* f, int mu)
+{
+    build_levels();
+    matrix_elements_for_jacobi a_h = jacobi_matrices[level - coarsest_level];
+    std::vector<float> v(v_inout, v_inout + a_h.size), fh(f, f + a_h.size);
+    std::vector<float> r = jacobirelaxation(g_q, a_h.a_lu_handle, a_h.size, v, fh, mu);
+    std::memcpy(v_inout, r.data(), r.size() * sizeof(float));
+}
+
+// the whole program: main()'s last lines P:725-727.  ~20-30 s single thread.
+long long ref_run_program(float* solution_out)
+{
+    build_levels();
+    std::vector<float> f_global = globalforcefunction();
+    std::vector<float> s = fullmultigrid(g_q, jacobi_matrices[jacobi_matrices.size() - 1], f_global);
+    std::memcpy(solution_out, s.data(), s.size() * sizeof(float));
+    return (long long)s.size();
+}
+
+}  // extern "C"
