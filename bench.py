@@ -263,7 +263,7 @@ def run_ours(args, rank, world, local_rank):
     pts = n * n if world == 1 else (mg.info(capi.MG_INFO_ROW_END, level) - mg.info(capi.MG_INFO_ROW_BEGIN, level)) * n
     kernels = {}
     reps = 20
-    algo = {"jacobi_sweep": (capi.MG_OP_SMOOTH1, 3.0), "residual": (capi.MG_OP_RESIDUAL, 3.0),
+    algo = {"jacobi_sweep": (capi.MG_OP_SMOOTH1, 3.0), "two_sweeps_one_launch": (capi.MG_OP_SMOOTH2, 3.0), "residual": (capi.MG_OP_RESIDUAL, 3.0),
             "residual_norm_only": (capi.MG_OP_RESIDUAL_NORM, 2.0), "restrict": (capi.MG_OP_RESTRICT, 1.25),
             "prolong_correct": (capi.MG_OP_PROLONG, 2.25)}
     for name, (op, s_per_pt) in algo.items():

@@ -381,6 +381,7 @@ void Ctx::cycle(int level, int nu1, int nu2, int gamma)
     auto key = std::make_tuple(level, nu1, nu2, gamma, parity_mask());
     auto it = graphs.find(key);
     if (it == graphs.end()) {
+        fused_pretune(*this, level, nu1, nu2);
         GraphEntry ge;
         const long long before = lc.n;
         cudaGraph_t g = nullptr;

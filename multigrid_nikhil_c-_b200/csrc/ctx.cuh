@@ -82,6 +82,7 @@ struct Ctx {
     double* h_norm = nullptr;  // pinned
     bool capturing = false;
     std::map<std::tuple<int, int, int, int, unsigned long long>, GraphEntry> graphs;
+    std::map<std::tuple<int, int, int, int>, int> stream_ry;  // tuned chunk height per (level, mode, NS, rbgs)
     Comm* comm = nullptr;
     int aggl_level = 0;  // levels <= aggl_level are replicated on every rank
     bool graph_dist = false;  // capture NCCL exchanges into cycle graphs (MGB200_GRAPH_DIST=1)

@@ -4,6 +4,8 @@
 #include "fused.cuh"
 
 #include <algorithm>
+#include <vector>
+#include <cstdlib>
 
 #include "comm.cuh"
 #include "stream.cuh"
@@ -12,13 +14,17 @@
 namespace mgb {
 
 static int g_num_sms = 148;
+static int g_force_ry = 0;
+static int g_force_ry_minN = 4096;
+static bool g_autotune = true;   // MGB200_AUTOTUNE=0 disables the chunk-height tuner
+static int g_occ = 12;  // resident streaming warps per SM (MGB200_STREAM_OCC), enforced by padding dynamic shared memory
 
 template <typename T, int NS, int MODE, bool RBGS>
 static void set_attr()
 {
     typedef StreamCfg<T, NS, MODE> C;
     MG_CK(cudaFuncSetAttribute(k_stream<T, NS, MODE, RBGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)C::SMEM_BYTES));
+                               (int)std::max<size_t>(C::SMEM_BYTES, 100 * 1024)));
 }
 
 template <typename T>
@@ -46,6 +52,10 @@ void fused_setup(Ctx& ctx)
     cudaDeviceProp prop;
     MG_CK(cudaGetDeviceProperties(&prop, ctx.device));
     g_num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("MGB200_STREAM_RY")) g_force_ry = atoi(e);
+    if (const char* e = getenv("MGB200_STREAM_RY_MINN")) g_force_ry_minN = atoi(e);
+    if (const char* e = getenv("MGB200_STREAM_OCC")) g_occ = std::max(1, atoi(e));
+    if (const char* e = getenv("MGB200_AUTOTUNE")) g_autotune = atoi(e) != 0;
     if (ctx.f64()) set_attrs_t<double>();
     else set_attrs_t<float>();
 }
@@ -53,8 +63,22 @@ void fused_setup(Ctx& ctx)
 // ---------------------------------------------------------------------------------
 // one launch of a streaming kernel on level lv (lcv = next coarser level for PRE/POST)
 // ---------------------------------------------------------------------------------
-template <typename T, int NS, int MODE, bool RBGS>
-static void launch_stream(Ctx& ctx, Level& lv, Level* lcv)
+template <typename T, int NS, int MODE>
+static int default_ry(const Level& lv, int strips)
+{
+    // One wave of g_occ warps per SM: a partial last wave costs a whole chunk time, so the chunk height is
+    // chosen to make strips x chunks land on one wave whenever that keeps chunks <= 256 rows.
+    const int rows = lv.own_hi - lv.own_lo;
+    const int wave = g_num_sms * g_occ;
+    const int chunks = std::max(1, wave / strips);
+    int ry = (rows + chunks - 1) / chunks;
+    ry = std::max(8, std::min(256, ry));
+    if (g_force_ry > 0 && lv.N >= g_force_ry_minN) ry = g_force_ry;   // MGB200_STREAM_RY[_MINN]: tuning knobs
+    return (ry + 1) & ~1;
+}
+
+template <typename T, int NS, int MODE>
+static StreamArgs<T> make_args(Ctx& ctx, Level& lv, Level* lcv, int ry)
 {
     typedef StreamCfg<T, NS, MODE> C;
     StreamArgs<T> a;
@@ -69,15 +93,10 @@ static void launch_stream(Ctx& ctx, Level& lv, Level* lcv)
     a.row_hi = lv.st_hi;
     const int rows = a.yb - a.ya;
     a.strips = std::max(1, (int)cdiv(std::max(1, lv.N - C::V * C::HLANES), C::OUTW));
-    // enough independent warps to fill the chip once; chunks of 16..128 rows
-    const int target = g_num_sms * 16;
-    int chunks = std::max(1, target / a.strips);
-    int ry = (rows + chunks - 1) / chunks;
-    ry = std::min(128, std::max(16, ry));
-    ry = (ry + 1) & ~1;
-    chunks = (rows + ry - 1) / ry;
+    a.strips_pad = (a.strips + kStreamWarps - 1) / kStreamWarps * kStreamWarps;
+    if (ry <= 0) ry = default_ry<T, NS, MODE>(lv, a.strips);
     a.ry = ry;
-    a.nitems = a.strips * chunks;
+    a.nitems = a.strips_pad * ((rows + ry - 1) / ry);
     const T om = (T)ctx.cfg.omega;
     a.c0 = (T)(1.0 - (double)om);
     a.c1 = (T)((double)om / 4.0);
@@ -88,28 +107,97 @@ static void launch_stream(Ctx& ctx, Level& lv, Level* lcv)
     a.pitch_c = 0;
     a.Nc = 0;
     a.crow_lo = a.crow_hi = 0;
-    // lazy halo exchanges (no-ops on replicated levels): rows the stencil pipeline reaches into
-    ctx.ensure_halo(lv, Ctx::W_U, C::HT - (MODE == MODE_POST ? 1 : 0));
-    ctx.ensure_halo(lv, Ctx::W_F, NS + (MODE == MODE_PRE ? 1 : 0) - (MODE == MODE_SWEEPS ? 1 : 0));
     if (MODE == MODE_PRE) {
-        lcv->cur = 0;
         a.fc = (T*)lcv->f;
         a.uc = (lv.distributed && !lcv->distributed) ? nullptr : (T*)lcv->u[0];
         a.pitch_c = lcv->pitch;
         a.Nc = lcv->N;
     } else if (MODE == MODE_POST) {
-        ctx.ensure_halo(*lcv, Ctx::W_U, NS / 2 + 1);
         a.ec = (const T*)lcv->u[lcv->cur];
         a.pitch_c = lcv->pitch;
         a.Nc = lcv->N;
         a.crow_lo = lcv->st_lo;
         a.crow_hi = lcv->st_hi;
     }
-    if (rows <= 0) return;
+    return a;
+}
+
+template <typename T, int NS, int MODE, bool RBGS>
+static void raw_launch(Ctx& ctx, const StreamArgs<T>& a)
+{
+    typedef StreamCfg<T, NS, MODE> C;
+    if (a.yb <= a.ya) return;
     const unsigned grid = cdiv(a.nitems, kStreamWarps);
-    k_stream<T, NS, MODE, RBGS><<<grid, kStreamWarps * 32, C::SMEM_BYTES, ctx.stream>>>(a);
+    // cap the resident warps per SM at g_occ by padding the dynamic shared memory
+    const size_t smem = std::min<size_t>(100 * 1024, std::max<size_t>(C::SMEM_BYTES, (size_t)(227 * 1024) / std::max(1, g_occ / kStreamWarps) - 1024));
+    k_stream<T, NS, MODE, RBGS><<<grid, kStreamWarps * 32, smem, ctx.stream>>>(a);
     ++ctx.lc.n;
     MG_CK(cudaGetLastError());
+}
+
+// Chunk height per (level, kernel): on the big levels the best height depends on how strips x chunks maps
+// onto waves and DRAM (measured spread at 4097^2: 79..117 us for the same kernel, profiles/r01_tune_stream.txt),
+// so it is picked once by timing a few candidates.  Tuning launches write only scratch state (the non-current
+// u buffer and, for PRE, the coarse f / zero guess that the real launch rewrites), results never depend on it.
+constexpr int kTuneMinN = 2048;
+
+template <typename T, int NS, int MODE, bool RBGS>
+static int tuned_ry(Ctx& ctx, Level& lv, Level* lcv)
+{
+    const auto key = std::make_tuple(lv.level, MODE, NS, (int)RBGS);
+    auto it = ctx.stream_ry.find(key);
+    if (it != ctx.stream_ry.end()) return it->second;
+    StreamArgs<T> a0 = make_args<T, NS, MODE>(ctx, lv, lcv, 0);
+    if (lv.N < kTuneMinN || ctx.capturing || !g_autotune || g_force_ry > 0) return a0.ry;
+    const int rows = lv.own_hi - lv.own_lo;
+    std::vector<int> cand;
+    auto add = [&](int ry) {
+        ry = (std::max(8, std::min(512, ry)) + 1) & ~1;
+        if (std::find(cand.begin(), cand.end(), ry) == cand.end()) cand.push_back(ry);
+    };
+    add(a0.ry);
+    for (int w : {8, 10, 12, 16}) {
+        const int chunks = std::max(1, g_num_sms * w / a0.strips);
+        const int ry = (rows + chunks - 1) / chunks;
+        if (ry <= 512) add(ry);
+    }
+    add(128); add(192); add(256);
+    cudaEvent_t e0, e1;
+    MG_CK(cudaEventCreate(&e0));
+    MG_CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    int best_ry = a0.ry;
+    for (int ry : cand) {
+        StreamArgs<T> a = make_args<T, NS, MODE>(ctx, lv, lcv, ry);
+        raw_launch<T, NS, MODE, RBGS>(ctx, a);
+        MG_CK(cudaEventRecord(e0, ctx.stream));
+        raw_launch<T, NS, MODE, RBGS>(ctx, a);
+        raw_launch<T, NS, MODE, RBGS>(ctx, a);
+        MG_CK(cudaEventRecord(e1, ctx.stream));
+        MG_CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        MG_CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) { best = ms; best_ry = ry; }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ctx.lc.n -= 3 * (long long)cand.size();   // tuning launches are not part of the work
+    ctx.stream_ry[key] = best_ry;
+    return best_ry;
+}
+
+template <typename T, int NS, int MODE, bool RBGS>
+static void launch_stream(Ctx& ctx, Level& lv, Level* lcv)
+{
+    typedef StreamCfg<T, NS, MODE> C;
+    // lazy halo exchanges (no-ops on replicated levels): rows the stencil pipeline reaches into
+    ctx.ensure_halo(lv, Ctx::W_U, C::HT - (MODE == MODE_POST ? 1 : 0));
+    ctx.ensure_halo(lv, Ctx::W_F, NS + (MODE == MODE_PRE ? 1 : 0) - (MODE == MODE_SWEEPS ? 1 : 0));
+    if (MODE == MODE_PRE) lcv->cur = 0;
+    if (MODE == MODE_POST) ctx.ensure_halo(*lcv, Ctx::W_U, NS / 2 + 1);
+    const int ry = tuned_ry<T, NS, MODE, RBGS>(ctx, lv, lcv);
+    const StreamArgs<T> a = make_args<T, NS, MODE>(ctx, lv, lcv, ry);
+    raw_launch<T, NS, MODE, RBGS>(ctx, a);
     lv.cur ^= 1;
     lv.hv_u = 0;
     if (MODE == MODE_PRE) {
@@ -239,6 +327,36 @@ bool fused_cycle_level(Ctx& ctx, int level, int nu1, int nu2, int gamma)
     if (ctx.f64()) post_fused<double>(ctx, lv, lcv, nu2);
     else post_fused<float>(ctx, lv, lcv, nu2);
     return true;
+}
+
+// Pick the chunk heights of every big level a cycle from `level` will visit, eagerly (cannot be done while
+// a CUDA graph is being captured).  Side-effect free for the solver state.
+template <typename T>
+static void pretune_t(Ctx& ctx, int level, int nu1, int nu2)
+{
+    for (int l = level; l > ctx.cfg.coarsest_level; --l) {
+        Level& lv = ctx.L(l);
+        Level& lcv = ctx.L(l - 1);
+        if (lv.N < kTuneMinN) break;
+        const bool rb = ctx.cfg.smoother == MG_SMOOTH_RBGS;
+        const int k1 = std::min(nu1, 2), k2 = std::min(nu2, 2);
+        if (!rb) {
+            if (k1 == 2) tuned_ry<T, 2, MODE_PRE, false>(ctx, lv, &lcv); else if (k1 == 1) tuned_ry<T, 1, MODE_PRE, false>(ctx, lv, &lcv);
+            if (k2 == 2) tuned_ry<T, 2, MODE_POST, false>(ctx, lv, &lcv); else if (k2 == 1) tuned_ry<T, 1, MODE_POST, false>(ctx, lv, &lcv);
+            if (nu1 - k1 >= 3 || nu2 - k2 >= 3) tuned_ry<T, 3, MODE_SWEEPS, false>(ctx, lv, nullptr);
+        } else {
+            if (k1 == 2) tuned_ry<T, 4, MODE_PRE, true>(ctx, lv, &lcv); else if (k1 == 1) tuned_ry<T, 2, MODE_PRE, true>(ctx, lv, &lcv);
+            if (k2 == 2) tuned_ry<T, 4, MODE_POST, true>(ctx, lv, &lcv); else if (k2 == 1) tuned_ry<T, 2, MODE_POST, true>(ctx, lv, &lcv);
+            if (nu1 - k1 >= 2 || nu2 - k2 >= 2) tuned_ry<T, 4, MODE_SWEEPS, true>(ctx, lv, nullptr);
+        }
+    }
+}
+
+void fused_pretune(Ctx& ctx, int level, int nu1, int nu2)
+{
+    if (!(ctx.cfg.flags & MG_FUSED) || nu1 < 1 || nu2 < 1) return;
+    if (ctx.f64()) pretune_t<double>(ctx, level, nu1, nu2);
+    else pretune_t<float>(ctx, level, nu1, nu2);
 }
 
 bool fused_time_hook(Ctx& ctx, int level, bool pre)

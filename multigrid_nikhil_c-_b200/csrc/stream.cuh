@@ -31,13 +31,16 @@
 //  - global pointers for prefetch and store advance by one pitch per step.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mgb {
 
 enum { MODE_SWEEPS = 0, MODE_PRE = 1, MODE_POST = 2 };
 
-constexpr int kStreamWarps = 1;  // warps (independent work items) per CTA: 1 => occupancy is bounded by registers, not by ring smem
+constexpr int kStreamWarps = 1;  // warps (independent work items) per CTA.  4 lock-stepped warps per CTA (bar.sync every 3 rows)
+                                 // were measured slower and more erratic (profiles/r01_tune_stream.txt)
 constexpr int kRingSlots = 12;   // 4 blocks x 3 slots
 
 template <typename T, int NS, int MODE>
@@ -72,6 +75,7 @@ struct StreamArgs {
     int row_lo, row_hi;  // rows backed by storage [row_lo, row_hi); anything else reads as zero
     int ry;              // output rows per chunk
     int strips;
+    int strips_pad;      // strips rounded up to a multiple of kStreamWarps
     int nitems;          // strips * chunks
     T c0, c1, w;
     T* fc;               // PRE: coarse right-hand side / zero guess
@@ -82,17 +86,19 @@ struct StreamArgs {
     int crow_lo, crow_hi;  // coarse rows backed by storage
 };
 
+// cp.async with the `ignore-src` predicate: when !valid nothing is read and zeros are written
+// (maps 1:1 onto LDGSTS.ZFILL with a predicate; `gmem` must still be a mapped address).
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid)
 {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    const int sz = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, %2, 0;\n\tcp.async.cg.shared.global [%0], [%1], 16, p;\n\t}\n"
+                 ::"r"(s), "l"(gmem), "r"((int)valid) : "memory");
 }
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid)
 {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    const int sz = valid ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, %2, 0;\n\tcp.async.ca.shared.global [%0], [%1], 8, p;\n\t}\n"
+                 ::"r"(s), "l"(gmem), "r"((int)valid) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
@@ -113,11 +119,16 @@ struct Streamer {
     T* cblk[4];
     int c;         // first column of this lane
     int y0, y1;
-    bool lane_ld, lane_ldc, lane_st, edge;  // per-lane load / store flags; warp-uniform "strip touches a boundary column"
-    bool cz[V];    // column must hold zero (Dirichlet ring / beyond the grid)
+    bool lane_ld, lane_ldc, lane_st;  // per-lane load / store flags
+    typedef typename std::conditional<sizeof(T) == 8, unsigned long long, unsigned>::type MaskT;
+    MaskT cm[V];   // all-ones for interior columns, 0 where the column must hold zero (Dirichlet ring / beyond the grid)
     const T* g_u;  // global prefetch pointers (row of the next prefetch, this lane's column)
     const T* g_f;
     T* g_o;        // output pointer of the row the last smoothing stage produces in this step
+    const T* g_c;  // POST: coarse row of the next prefetch
+    const T* safe_u;  // mapped addresses handed to ignored copies
+    const T* safe_f;
+    const T* safe_c;
 
     T W[C::NW > 0 ? C::NW : 1][3][V];
     T WL[C::NW > 0 ? C::NW : 1][3], WR[C::NW > 0 ? C::NW : 1][3];
@@ -150,15 +161,16 @@ struct Streamer {
         constexpr int b = REL / 3, s = REL % 3;
         T* dst = blk[b & 3] + s * C::SLOT_ELEMS;
         const bool v = lane_ld && (y >= a.row_lo) && (y < a.row_hi);
-        cp_async16(dst, v ? g_u : a.u_in + (i64)a.row_lo * a.pitch, v);
-        cp_async16(dst + 32 * V, v ? g_f : a.f + (i64)a.row_lo * a.pitch, v);
+        cp_async16(dst, v ? g_u : safe_u, v);
+        cp_async16(dst + 32 * V, v ? g_f : safe_f, v);
         g_u += a.pitch;
         g_f += a.pitch;
         if (MODE == MODE_POST) {
+            // coarse row ceil(y/2): a new one starts at every odd y; even rows re-read the previous one (L1 hit)
             const int ic = (y + 1) >> 1;
             const bool vc = lane_ldc && (ic >= a.crow_lo) && (ic < a.crow_hi) && (y >= 0);
-            const T* src = a.ec + (vc ? ((i64)ic * a.pitch_c + (c >> 1)) : (i64)a.crow_lo * a.pitch_c);
-            cp_async8(cblk[b & 3] + s * C::CSLOT_ELEMS, src, vc);
+            cp_async8(cblk[b & 3] + s * C::CSLOT_ELEMS, vc ? g_c : safe_c, vc);
+            if (!(y & 1)) g_c += a.pitch_c;   // ceil((y+1)/2) > ceil(y/2) exactly when y is even
         }
         cp_async_commit();
     }
@@ -174,15 +186,18 @@ struct Streamer {
 
     // Dirichlet ring: only rows 0 / N (rows beyond them are zero by construction) and, on
     // strips touching the boundary, the columns flagged in cz[] ever need forcing.
-    __device__ __forceinline__ void mask_row(int row, T (&o)[V]) const
+    // Dirichlet columns: AND with a per-lane bit mask (all-ones in the interior; exact, NaN-safe, gives +0).
+    // Dirichlet rows 0 / N are handled by a warp-uniform branch around each stage (rows beyond them are
+    // zero by construction), so interior rows pay two logic ops per value and nothing else.
+    __device__ __forceinline__ void mask_cols(T (&o)[V]) const
     {
-        const bool rowbad = (row <= 0) || (row >= a.N);
-        if (rowbad || edge) {
 #pragma unroll
-            for (int k = 0; k < V; ++k)
-                if (rowbad || cz[k]) o[k] = (T)0;
+        for (int k = 0; k < V; ++k) {
+            if constexpr (sizeof(T) == 8) o[k] = __longlong_as_double((long long)((unsigned long long)__double_as_longlong(o[k]) & cm[k]));
+            else o[k] = __uint_as_float(__float_as_uint(o[k]) & cm[k]);
         }
     }
+    __device__ __forceinline__ bool ring_row(int row) const { return (row <= 0) || (row >= a.N); }
 
     // one pipeline step: row y of the input arrives
     template <int PH>
@@ -216,8 +231,8 @@ struct Streamer {
                 }
             }
 #pragma unroll
-            for (int k = 0; k < V; ++k) cur[k] = cur[k] + e[k];                                // P:623
-            mask_row(y, cur);
+            for (int k = 0; k < V; ++k) cur[k] = ring_row(y) ? (T)0 : cur[k] + e[k];           // P:623
+            mask_cols(cur);
         }
         put_row<NEW>(0, cur);
 
@@ -230,19 +245,24 @@ struct Streamer {
             else if (s == 2) ldv<T>(rslot<PH, 2>() + 32 * V, ff);
             else if (s == 3) ldv<T>(rslot<PH, 3>() + 32 * V, ff);
             else ldv<T>(rslot<PH, 4>() + 32 * V, ff);
+            if (ring_row(rs)) {   // warp-uniform, rare
 #pragma unroll
-            for (int k = 0; k < V; ++k) {
-                const T l = (k == 0) ? WL[s - 1][MID] : W[s - 1][MID][k - 1];
-                const T r = (k == V - 1) ? WR[s - 1][MID] : W[s - 1][MID][k + 1];
-                const T sig = sigma4<T>(W[s - 1][OLD][k], W[s - 1][NEW][k], l, r);
-                if (RBGS) {
-                    const int colour = (s - 1) & 1;
-                    o[k] = (((rs + c + k) & 1) == colour) ? gs_pt<T>(ff[k], sig) : W[s - 1][MID][k];
-                } else {
-                    o[k] = jacobi_pt<T>(a.c0, a.c1, W[s - 1][MID][k], ff[k], sig);
+                for (int k = 0; k < V; ++k) o[k] = (T)0;
+            } else {
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const T l = (k == 0) ? WL[s - 1][MID] : W[s - 1][MID][k - 1];
+                    const T r = (k == V - 1) ? WR[s - 1][MID] : W[s - 1][MID][k + 1];
+                    const T sig = sigma4<T>(W[s - 1][OLD][k], W[s - 1][NEW][k], l, r);
+                    if (RBGS) {
+                        const int colour = (s - 1) & 1;
+                        o[k] = (((rs + c + k) & 1) == colour) ? gs_pt<T>(ff[k], sig) : W[s - 1][MID][k];
+                    } else {
+                        o[k] = jacobi_pt<T>(a.c0, a.c1, W[s - 1][MID][k], ff[k], sig);
+                    }
                 }
+                mask_cols(o);
             }
-            mask_row(rs, o);
             if (s < C::NW) put_row<NEW>(s, o);
             if (s == NS) {
                 if (lane_st && rs >= y0 && rs < y1) stv<T>(g_o, o);
@@ -255,13 +275,18 @@ struct Streamer {
             const int rr = y - NS - 1;
             T ff[V], o[V];
             ldv<T>(rslot<PH, NS + 1>() + 32 * V, ff);
+            if (ring_row(rr)) {
 #pragma unroll
-            for (int k = 0; k < V; ++k) {
-                const T l = (k == 0) ? WL[NS][MID] : W[NS][MID][k - 1];
-                const T r = (k == V - 1) ? WR[NS][MID] : W[NS][MID][k + 1];
-                o[k] = resid_pt<T>(W[NS][MID][k], ff[k], sigma4<T>(W[NS][OLD][k], W[NS][NEW][k], l, r));
+                for (int k = 0; k < V; ++k) o[k] = (T)0;
+            } else {
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const T l = (k == 0) ? WL[NS][MID] : W[NS][MID][k - 1];
+                    const T r = (k == V - 1) ? WR[NS][MID] : W[NS][MID][k + 1];
+                    o[k] = resid_pt<T>(W[NS][MID][k], ff[k], sigma4<T>(W[NS][OLD][k], W[NS][NEW][k], l, r));
+                }
+                mask_cols(o);
             }
-            mask_row(rr, o);
 #pragma unroll
             for (int k = 0; k < V; ++k) R[NEW][k] = o[k];
             RL[NEW] = __shfl_up_sync(FULL, o[V - 1], 1);
@@ -276,10 +301,14 @@ struct Streamer {
                     const T sw = (k == 0) ? RL[NEW] : R[NEW][k - 1];
                     oc[j] = fw_pt<T>(a.w, nw, R[OLD][k + 1], sw, R[NEW][k + 1], wv, R[MID][k + 1],
                                      R[OLD][k], R[NEW][k], R[MID][k]);
-                    if (edge) {
-                        const int J = (c + k) >> 1;
-                        if (!(J >= 1 && J < a.Nc)) oc[j] = (T)0;
-                    }
+                }
+                {   // coarse ring columns: J = 0 <=> fine column 0, J >= Nc <=> fine column >= N (same mask)
+                    T tmp[V];
+#pragma unroll
+                    for (int k = 0; k < V; ++k) tmp[k] = (k & 1) ? (T)0 : oc[k >> 1];
+                    mask_cols(tmp);
+#pragma unroll
+                    for (int j = 0; j < H; ++j) oc[j] = tmp[2 * j];
                 }
                 if (lane_st && yc >= y0 && yc < y1) {
                     const i64 offc = (i64)(yc >> 1) * a.pitch_c + (c >> 1);
@@ -306,8 +335,9 @@ struct Streamer {
 
     __device__ __forceinline__ void run(T* ring_base, int warp, int lane, int item)
     {
-        const int chunk = item / a.strips;
-        const int strip = item - chunk * a.strips;
+        const int chunk = item / a.strips_pad;
+        const int strip = item - chunk * a.strips_pad;
+        const bool dead = strip >= a.strips;   // padding warp (only when kStreamWarps > 1): neither loads nor stores
         const int X0 = strip * C::OUTW;
         c = X0 + V * lane;
         const int out_lo = (strip == 0) ? 0 : X0 + V * C::HLANES;
@@ -317,12 +347,11 @@ struct Streamer {
         ring = ring_base + (size_t)warp * C::WARP_ELEMS + lane * V;
         cring = ring_base + (size_t)warp * C::WARP_ELEMS + C::DEPTH * C::SLOT_ELEMS + lane * H;
         const int ylo = y0 - C::HT, yhi = y1 - 1 + C::HB;
-        lane_ld = (c < a.pitch);
-        lane_ldc = ((c >> 1) < a.pitch_c);
-        lane_st = (c >= out_lo) && (c < out_hi) && (c < a.N);
-        edge = (strip == 0) || (X0 + 32 * V >= a.N);
+        lane_ld = (c < a.pitch) && !dead;
+        lane_ldc = ((c >> 1) < a.pitch_c) && !dead;
+        lane_st = (c >= out_lo) && (c < out_hi) && (c < a.N) && !dead;
 #pragma unroll
-        for (int k = 0; k < V; ++k) cz[k] = (c + k < 1) || (c + k >= a.N);
+        for (int k = 0; k < V; ++k) cm[k] = ((c + k < 1) || (c + k >= a.N)) ? (MaskT)0 : ~(MaskT)0;
 
 #pragma unroll
         for (int s = 0; s < (C::NW > 0 ? C::NW : 1); ++s)
@@ -343,6 +372,14 @@ struct Streamer {
         g_u = a.u_in + (i64)ylo * a.pitch + c;
         g_f = a.f + (i64)ylo * a.pitch + c;
         g_o = a.u_out + (i64)(ylo - NS) * a.pitch + c;   // row produced by stage NS in the first step
+        safe_u = a.u_in + (i64)a.row_lo * a.pitch;
+        safe_f = a.f + (i64)a.row_lo * a.pitch;
+        safe_c = a.ec;
+        g_c = a.ec;
+        if (MODE == MODE_POST) {
+            safe_c = a.ec + (i64)a.crow_lo * a.pitch_c;
+            g_c = a.ec + (i64)((ylo + 1) >> 1) * a.pitch_c + (c >> 1);
+        }
 
         // prologue: rows ylo .. ylo+D-1 into slots 0 .. D-1
         set_blocks(0);
@@ -381,7 +418,6 @@ k_stream(const StreamArgs<T> a)
     extern __shared__ __align__(16) unsigned char stream_smem[];
     const int warp = threadIdx.x >> 5;
     const int item = blockIdx.x * kStreamWarps + warp;
-    if (item >= a.nitems) return;  // warp-uniform
     Streamer<T, NS, MODE, RBGS> st(a);
     st.run(reinterpret_cast<T*>(stream_smem), warp, threadIdx.x & 31, item);
 }
