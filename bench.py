@@ -227,12 +227,24 @@ def run_ours(args, rank, world, local_rank):
 
     mg = mgb200.Multigrid(level, dtype=dtype, smoother=args.smoother, device=local_rank, rank=rank, world=world,
                           comm_id=comm, graph=not args.no_graph, fused=not args.no_fused,
-                          coarse_tail=not args.no_tail)
-    f_t, f_host = pinned(n * n, dtype)
-    u_t, u_host = pinned(n * n, dtype)
-    f_host[:] = synthetic_rhs(level, dtype)
-    u_host[:] = 0
-    mg.set_rhs(level, f_host)
+                          coarse_tail=not args.no_tail, agglomerate_level=args.aggl)
+    slab = world > 1 and not args.full_host_vectors
+    if slab:
+        # a rank only ever touches the interior rows it stores: keep just those on the host (Multigrid.set_rhs_slab)
+        ya, yb = mg.slab_rows(level)
+        f_t, f_host = pinned((yb - ya) * n, dtype)
+        u_t, u_host = pinned((yb - ya) * n, dtype)
+        h = 1.0 / (1 << level)
+        rng = np.random.default_rng(1234 + ya)          # depends on the rows, not on the rank count
+        f_host[:] = (h * h * rng.uniform(-1.0, 1.0, (yb - ya) * n)).astype(dtype)
+        u_host[:] = 0
+        mg.set_rhs_slab(level, f_host)
+    else:
+        f_t, f_host = pinned(n * n, dtype)
+        u_t, u_host = pinned(n * n, dtype)
+        f_host[:] = synthetic_rhs(level, dtype)
+        u_host[:] = 0
+        mg.set_rhs(level, f_host)
     mg.zero_u(level)
     upd = updates_per_cycle(level, 1, nu1, nu2, gamma)
 
@@ -310,20 +322,26 @@ def run_ours(args, rank, world, local_rank):
                 "cycle_ms_from_level_down": level_ms}
 
     # ---- end to end through the reference-shaped host call (P:575 on host vectors) ----
-    mg.set_rhs(level, f_host)
-    e2e_steps = max(3, min(K, 10))
+    def e2e_call():
+        if slab:
+            mg.vcyclemultigrid_slab(level, u_host, f_host, nu1, nu2, gamma)
+        else:
+            mg.vcyclemultigrid(u_host, f_host, nu1, nu2, gamma, inplace=True)
+
+    e2e_steps = max(3, min(K, 10)) if not args.no_e2e else 1
     u_host[:] = 0
     for _ in range(2):
-        mg.vcyclemultigrid(u_host, f_host, nu1, nu2, gamma, inplace=True)
+        e2e_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        mg.vcyclemultigrid(u_host, f_host, nu1, nu2, gamma, inplace=True)
+        e2e_call()
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
     rows = n if world == 1 else (mg.info(capi.MG_INFO_ROW_END, level) - mg.info(capi.MG_INFO_ROW_BEGIN, level))
     e2e = {"value": upd / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
-           "h2d_bytes_per_step": 2 * (rows + 2) * n * esize, "d2h_bytes_per_step": rows * n * esize,
+           "h2d_bytes_per_step": 2 * (n if world == 1 else mg.slab_rows(level)[1] - mg.slab_rows(level)[0]) * n * esize,
+           "d2h_bytes_per_step": rows * n * esize,
            "call": "mg_host_vcyclemultigrid (vcyclemultigrid P:575 on pinned host vectors)"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -332,9 +350,10 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": f"{n + 2}^2 {'fp64' if esize == 8 else 'fp32'} V({nu1},{nu2}) gamma={gamma} "
                                    f"{args.smoother}, full weighting / bilinear, coarsened to 3x3"
                                    + ("" if world == 1 else f", row slabs over {world} GPUs"),
-                       "level": level, "rhs": "h^2*U(-1,1) rng(1234)", "updates_per_cycle": upd,
+                       "level": level, "rhs": "h^2*U(-1,1) rng(1234)" if not slab else "h^2*U(-1,1), rng seeded per row slab", "updates_per_cycle": upd,
                        "l2_policy": "inputs larger than L2 (4 arrays x %.0f MB on the finest level)" % (n * n * esize / 1e6),
-                       "regions": regions, "region_stat": "median", "flags": {"graph": not args.no_graph,
+                       "regions": regions, "region_stat": "median", "agglomerate_level": mg.info(capi.MG_INFO_AGGLOMERATE_LEVEL, level) if world > 1 else None,
+                       "flags": {"graph": not args.no_graph,
                                                                               "fused": not args.no_fused,
                                                                               "coarse_tail": not args.no_tail}},
             "finest_points_per_s": n * n / (ms_step * 1e-3),
@@ -365,6 +384,10 @@ def main():
     ap.add_argument("--no-fused", action="store_true")
     ap.add_argument("--no-tail", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--aggl", type=int, default=0, help="agglomeration level for N>1 (0 = library default)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (tuning runs)")
+    ap.add_argument("--full-host-vectors", action="store_true",
+                    help="N>1: every rank holds the full-grid host vectors (default: only the rows of its slab)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -76,7 +76,8 @@ int mg_slab_rows(int level, int rank, int world, int* row_begin, int* row_end);
 int mg_get_info(const mg_ctx* ctx, int what, int level, int64_t* out);
 enum { MG_INFO_PITCH = 0, MG_INFO_ROWS_STORED = 1, MG_INFO_ROW_BEGIN = 2, MG_INFO_ROW_END = 3,
        MG_INFO_LAUNCHES = 4, MG_INFO_DISTRIBUTED = 5, MG_INFO_BYTES_ALLOCATED = 6,
-       MG_INFO_GRAPH_LAUNCHES = 7, MG_INFO_AGGLOMERATE_LEVEL = 8 };
+       MG_INFO_GRAPH_LAUNCHES = 7, MG_INFO_AGGLOMERATE_LEVEL = 8,
+       MG_INFO_STORED_ROW_BEGIN = 9, MG_INFO_STORED_ROW_END = 10 /* owned + halo / ring rows kept by this rank */ };
 
 /* ---- data movement; host vectors are FULL-grid interior vectors (n*n), each rank
  *      takes / fills the rows of its slab (mg_get_* gathers nothing across ranks:

@@ -17,7 +17,8 @@ MG_SMOOTH_JACOBI, MG_SMOOTH_RBGS = 0, 1
 MG_GRAPH, MG_FUSED, MG_COARSE_TAIL = 1, 2, 4
 MG_COMM_ID_BYTES = 128
 (MG_INFO_PITCH, MG_INFO_ROWS_STORED, MG_INFO_ROW_BEGIN, MG_INFO_ROW_END, MG_INFO_LAUNCHES,
- MG_INFO_DISTRIBUTED, MG_INFO_BYTES_ALLOCATED, MG_INFO_GRAPH_LAUNCHES, MG_INFO_AGGLOMERATE_LEVEL) = range(9)
+ MG_INFO_DISTRIBUTED, MG_INFO_BYTES_ALLOCATED, MG_INFO_GRAPH_LAUNCHES, MG_INFO_AGGLOMERATE_LEVEL,
+ MG_INFO_STORED_ROW_BEGIN, MG_INFO_STORED_ROW_END) = range(11)
 (MG_OP_SMOOTH1, MG_OP_RESIDUAL, MG_OP_RESTRICT, MG_OP_PROLONG, MG_OP_PRE_FUSED, MG_OP_POST_FUSED,
  MG_OP_RESIDUAL_NORM, MG_OP_SMOOTH2) = range(8)
 

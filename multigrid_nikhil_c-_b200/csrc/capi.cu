@@ -133,6 +133,8 @@ int mg_get_info(const mg_ctx* c, int what, int level, int64_t* out)
             case MG_INFO_BYTES_ALLOCATED: *out = (int64_t)x.bytes_allocated; break;
             case MG_INFO_GRAPH_LAUNCHES: *out = x.graph_launches; break;
             case MG_INFO_AGGLOMERATE_LEVEL: *out = x.aggl_level; break;
+            case MG_INFO_STORED_ROW_BEGIN: *out = x.L(level).st_lo; break;
+            case MG_INFO_STORED_ROW_END: *out = x.L(level).st_hi; break;
             default: throw MgError(MG_ERR_ARG, "unknown info key");
         }
     });

@@ -141,6 +141,42 @@ class Multigrid:
     def get_r(self, level: int, out=None) -> np.ndarray:
         return self._get(self._lib.mg_get_r_host, level, out)
 
+    # -- row-slab host buffers (multi-GPU): the C ABI takes FULL-grid host vectors but a rank only
+    #    touches the interior rows it stores, [ya, yb).  A caller that holds just those rows passes the
+    #    address the full vector would have had: base = slab - (ya-1)*n*itemsize. ------------------
+    def slab_rows(self, level: int):
+        """1-based interior rows [ya, yb) that set_*/get_* of this rank read or write."""
+        n = self.side(level)
+        ya = max(self.info(capi.MG_INFO_STORED_ROW_BEGIN, level), 1)
+        yb = min(self.info(capi.MG_INFO_STORED_ROW_END, level), n + 1)
+        return ya, yb
+
+    def _slab_base(self, level: int, slab: np.ndarray) -> ctypes.c_void_p:
+        n = self.side(level)
+        ya, yb = self.slab_rows(level)
+        if slab.dtype != self.dtype or not slab.flags.c_contiguous or slab.size != (yb - ya) * n:
+            raise ValueError(f"slab buffer must be C-contiguous {self.dtype} with {(yb - ya) * n} entries (rows {ya}..{yb - 1})")
+        off = (ya - 1) * n * self.dtype.itemsize
+        base = slab.ctypes.data - off
+        if base <= 0:
+            raise ValueError("slab base address underflow")
+        return ctypes.c_void_p(base)
+
+    def set_rhs_slab(self, level: int, slab: np.ndarray):
+        self._ck(self._lib.mg_set_rhs_host(self._ctx, level, self._slab_base(level, slab)))
+
+    def set_u_slab(self, level: int, slab: np.ndarray):
+        self._ck(self._lib.mg_set_u_host(self._ctx, level, self._slab_base(level, slab)))
+
+    def get_u_slab(self, level: int, slab: np.ndarray):
+        """Fills the owned rows inside `slab` (halo rows of the buffer are left untouched)."""
+        self._ck(self._lib.mg_get_u_host(self._ctx, level, self._slab_base(level, slab)))
+
+    def vcyclemultigrid_slab(self, level: int, u_slab: np.ndarray, f_slab: np.ndarray, nu1=2, nu2=2, gamma=1):
+        """mg_host_vcyclemultigrid (P:575) on slab-sized host buffers: u_slab is in/out."""
+        self._ck(self._lib.mg_host_vcyclemultigrid(self._ctx, level, self._slab_base(level, u_slab),
+                                                   self._slab_base(level, f_slab), nu1, nu2, gamma))
+
     def zero_u(self, level: int):
         self._ck(self._lib.mg_zero_u(self._ctx, level))
 
