@@ -58,7 +58,8 @@ Ctx::Ctx(const mg_config& c) : cfg(c)
     if (cfg.world > 1) {
         int min_dist = 3;
         while (((i64)1 << min_dist) / cfg.world < 8) ++min_dist;
-        aggl_level = cfg.agglomerate_level > 0 ? cfg.agglomerate_level : std::min(cfg.finest_level - 1, 11);
+        // default 10: measured best at 8 GPUs on 16385^2 (profiles/r01_scaling_16385.md: 0.764 ms vs 0.779 at 11, 0.998 at 12)
+        aggl_level = cfg.agglomerate_level > 0 ? cfg.agglomerate_level : std::min(cfg.finest_level - 1, 10);
         aggl_level = std::max(aggl_level, min_dist - 1);
         aggl_level = std::max(aggl_level, cfg.coarsest_level - 1);
         MG_REQUIRE(aggl_level < cfg.finest_level || cfg.finest_level < min_dist,

@@ -1,0 +1,126 @@
+"""CPU dry run of bench.py's control flow with a stub context (no GPU here): catches Python
+errors in the harness and checks the JSON contract (keys the driver reads).  The numbers are
+fake; the real ones come from the B200 run."""
+import argparse
+import io
+import json
+import contextlib
+
+import numpy as np
+import pytest
+
+import bench
+
+
+class StubMG:
+    """Mimics the slice of multigrid_nikhil_c-_b200.Multigrid that bench.py uses."""
+
+    def __init__(self, level, dtype=np.float64, rank=0, world=1, **kw):
+        self.level, self.dtype, self.rank, self.world = level, np.dtype(dtype), rank, world
+        self._launches = 0
+        n = (1 << level) - 1
+        rows = (n + 1) // world
+        self.own = (max(1, rank * rows), (rank + 1) * rows if rank < world - 1 else n + 1)
+
+    def side(self, level):
+        return (1 << level) - 1
+
+    def slab_rows(self, level):
+        return max(self.own[0] - 6, 1), min(self.own[1] + 6, self.side(level) + 1)
+
+    def info(self, what, level=0):
+        from mgb200 import capi
+        return {capi.MG_INFO_ROW_BEGIN: self.own[0], capi.MG_INFO_ROW_END: self.own[1],
+                capi.MG_INFO_AGGLOMERATE_LEVEL: 11}.get(what, 0)
+
+    @property
+    def launches(self):
+        return self._launches
+
+    def set_rhs(self, level, f):
+        assert f.size == self.side(level) ** 2
+
+    def set_rhs_slab(self, level, slab):
+        ya, yb = self.slab_rows(level)
+        assert slab.size == (yb - ya) * self.side(level)
+
+    def zero_u(self, level):
+        pass
+
+    def time_cycle(self, level, nu1, nu2, gamma, reps):
+        self._launches += 13 * reps
+        return 0.3 * reps * 4.0 ** (level - 12)
+
+    def time_op(self, op, level, reps):
+        from mgb200 import capi
+        if op == capi.MG_OP_POST_FUSED:
+            raise capi.MgError(3, "not available")
+        return 0.08 * reps
+
+    def vcyclemultigrid(self, u, f, nu1, nu2, gamma, inplace=False):
+        assert inplace and u.size == f.size
+        return u
+
+    def vcyclemultigrid_slab(self, level, u, f, nu1, nu2, gamma):
+        assert u.size == f.size
+
+    def close(self):
+        pass
+
+
+def _args(**kw):
+    d = dict(gpus=1, steps=3, warmup=1, impl="ours", level=6, dtype="f64", smoother="jacobi", nu1=2, nu2=2, gamma=1,
+             no_graph=False, no_fused=False, no_tail=False, no_cpu=True, aggl=0, no_e2e=False, full_host_vectors=False)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+REQUIRED = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks"]
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_bench_control_flow_and_json_contract(monkeypatch, world):
+    import torch
+    import mgb200
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(mgb200, "Multigrid", StubMG)
+    monkeypatch.setattr(mgb200, "comm_id", lambda: bytes(128))
+    monkeypatch.setattr(bench, "pinned", lambda nelem, dtype: (None, np.empty(nelem, dtype=dtype)))
+    monkeypatch.setattr(bench, "ClockSampler", lambda dev: type("S", (), {"start": lambda s: None, "stop": lambda s: {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 1}})())
+    if world > 1:
+        import torch.distributed as dist
+        monkeypatch.setattr(dist, "init_process_group", lambda *a, **k: None)
+        monkeypatch.setattr(dist, "broadcast_object_list", lambda *a, **k: None)
+        monkeypatch.setattr(dist, "barrier", lambda *a, **k: None)
+        monkeypatch.setattr(dist, "all_reduce", lambda *a, **k: None)
+        monkeypatch.setattr(dist, "destroy_process_group", lambda *a, **k: None)
+        monkeypatch.setattr(torch, "tensor", lambda data, **k: torch.as_tensor(np.asarray(data, dtype=np.float64)))
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        bench.run_ours(_args(gpus=world, level=7 if world > 1 else 6), rank=0, world=world, local_rank=0)
+    lines = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in REQUIRED:
+        assert k in d, k
+    assert d["metric"] == bench.METRIC and d["higher_is_better"] is True and d["n_gpus"] == world
+    assert set(["bound", "achieved", "peak", "unit", "frac", "traffic"]) <= set(d["roofline"])
+    assert set(["value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"]) <= set(d["e2e"])
+    assert d["gpu_launches"] > 0 and "workload" in d["config"]
+
+
+def test_updates_per_cycle_matches_survey():
+    assert bench.updates_per_cycle(12, 1, 2, 2) == 89413008
+    assert bench.updates_per_cycle(8, 1, 2, 2, gamma=2) > bench.updates_per_cycle(8, 1, 2, 2)
+
+
+def test_reference_arm_line(capsys):
+    bench.run_reference(_args(impl="reference", level=6, steps=2, warmup=1), rank=0, world=1)
+    d = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
+    bench.run_reference(_args(impl="reference", level=6), rank=1, world=2)    # other ranks print nothing
+    assert capsys.readouterr().out == ""
