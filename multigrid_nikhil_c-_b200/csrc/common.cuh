@@ -12,9 +12,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "formulas.h"
+
 namespace mgb {
 
-typedef long long i64;
 
 template <typename T> struct Vec;
 template <> struct Vec<double> { static constexpr int N = 2; typedef double2 type; };
@@ -39,26 +40,6 @@ template <> __device__ __forceinline__ void stv<double>(double* p, const double 
 template <> __device__ __forceinline__ void stv<float>(float* p, const float (&v)[4])
 {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-}
-
-// The three point formulas.  Evaluation order is the parity contract with the oracle
-// (oracle/mg_oracle_impl.inc); the library is compiled with
-// --fmad=false so none of these contracts into an FMA.
-//   Sigma = (up + down) + (left + right)
-template <typename T> __device__ __forceinline__ T sigma4(T up, T dn, T lf, T rt) { return (up + dn) + (lf + rt); }
-// weighted Jacobi, P:138-142: ((1-w) v + (w/4) f) + (w/4) Sigma
-template <typename T> __device__ __forceinline__ T jacobi_pt(T c0, T c1, T v, T f, T sig) { return (c0 * v + c1 * f) + c1 * sig; }
-// Gauss-Seidel point update: 0.25 (f + Sigma)
-template <typename T> __device__ __forceinline__ T gs_pt(T f, T sig) { return (T)0.25 * (f + sig); }
-// residual, P:604-607: f - (4 v - Sigma)
-template <typename T> __device__ __forceinline__ T resid_pt(T v, T f, T sig) { return f - ((T)4 * v - sig); }
-// full weighting, P:539-542: w (((NW+NE+SW+SE) + 2 (W+E+N+S)) + 4 C), left to right
-template <typename T>
-__device__ __forceinline__ T fw_pt(T w, T nw, T ne, T sw, T se, T wv, T ev, T nv, T sv, T cv)
-{
-    T corners = ((nw + ne) + sw) + se;
-    T edges = ((wv + ev) + nv) + sv;
-    return w * ((corners + (T)2 * edges) + (T)4 * cv);
 }
 
 }  // namespace mgb

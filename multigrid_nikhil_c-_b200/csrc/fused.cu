@@ -10,12 +10,15 @@
 #include "comm.cuh"
 #include "stream.cuh"
 #include "tail.cuh"
+#include "tile.cuh"
 
 namespace mgb {
 
 static int g_num_sms = 148;
 static int g_force_ry = 0;
 static int g_force_ry_minN = 4096;
+static bool g_tile = false;      // MGB200_TILE=1: shared-memory tile kernels on the mid levels (experimental, see tile.cuh)
+static int g_tile_maxN = 1024;
 static bool g_autotune = true;   // MGB200_AUTOTUNE=0 disables the chunk-height tuner
 static int g_occ = 12;  // resident streaming warps per SM (MGB200_STREAM_OCC), enforced by padding dynamic shared memory
 
@@ -56,6 +59,8 @@ void fused_setup(Ctx& ctx)
     if (const char* e = getenv("MGB200_STREAM_RY_MINN")) g_force_ry_minN = atoi(e);
     if (const char* e = getenv("MGB200_STREAM_OCC")) g_occ = std::max(1, atoi(e));
     if (const char* e = getenv("MGB200_AUTOTUNE")) g_autotune = atoi(e) != 0;
+    if (const char* e = getenv("MGB200_TILE")) g_tile = atoi(e) != 0;
+    if (const char* e = getenv("MGB200_TILE_MAXN")) g_tile_maxN = atoi(e);
     if (ctx.f64()) set_attrs_t<double>();
     else set_attrs_t<float>();
 }
@@ -213,6 +218,79 @@ static void launch_stream(Ctx& ctx, Level& lv, Level* lcv)
     }
 }
 
+// ---------------------------------------------------------------------------------
+// shared-memory tile kernels for the mid levels (tile_core.h); same contract as launch_stream
+// ---------------------------------------------------------------------------------
+template <typename T, int NS, int MODE, bool RBGS, int TY, int TX>
+static void launch_tile_cfg(Ctx& ctx, Level& lv, Level* lcv)
+{
+    typedef TileCfg<T, NS, MODE, TY, TX> C;
+    static bool attr_set = false;
+    const size_t smem = (size_t)C::SMEM_ELEMS * sizeof(T);
+    if (!attr_set) {
+        MG_CK(cudaFuncSetAttribute(k_tile<T, NS, MODE, RBGS, TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    TileArgs<T> a;
+    a.u_in = (const T*)lv.u[lv.cur];
+    a.u_out = (T*)lv.u[lv.cur ^ 1];
+    a.f = (const T*)lv.f;
+    a.pitch = lv.pitch;
+    a.N = lv.N;
+    a.ya = lv.own_lo;
+    a.yb = lv.own_hi;
+    a.row_lo = lv.st_lo;
+    a.row_hi = lv.st_hi;
+    const T om = (T)ctx.cfg.omega;
+    a.c0 = (T)(1.0 - (double)om);
+    a.c1 = (T)((double)om / 4.0);
+    a.w = (T)ctx.cfg.restrict_weight;
+    a.fc = nullptr; a.uc = nullptr; a.ec = nullptr; a.pitch_c = 0; a.Nc = 0; a.crow_lo = a.crow_hi = 0;
+    if (MODE == TILE_PRE) {
+        a.fc = (T*)lcv->f;
+        a.uc = (lv.distributed && !lcv->distributed) ? nullptr : (T*)lcv->u[0];
+        a.pitch_c = lcv->pitch;
+        a.Nc = lcv->N;
+    } else if (MODE == TILE_POST) {
+        a.ec = (const T*)lcv->u[lcv->cur];
+        a.pitch_c = lcv->pitch;
+        a.Nc = lcv->N;
+        a.crow_lo = lcv->st_lo;
+        a.crow_hi = lcv->st_hi;
+    }
+    if (a.yb <= a.ya) return;
+    dim3 grid(cdiv(lv.N, TX), cdiv(a.yb - a.ya, TY));
+    k_tile<T, NS, MODE, RBGS, TY, TX><<<grid, kTileThreads, smem, ctx.stream>>>(a);
+    ++ctx.lc.n;
+    MG_CK(cudaGetLastError());
+}
+
+template <typename T, int NS, int MODE, bool RBGS>
+static void launch_tile(Ctx& ctx, Level& lv, Level* lcv)
+{
+    // same halo contract as the streaming kernels (MODE values coincide)
+    ctx.ensure_halo(lv, Ctx::W_U, NS + (MODE == TILE_PRE ? 2 : 0));
+    ctx.ensure_halo(lv, Ctx::W_F, NS + (MODE == TILE_PRE ? 1 : 0) - (MODE == TILE_SWEEPS ? 1 : 0));
+    if (MODE == TILE_PRE) lcv->cur = 0;
+    if (MODE == TILE_POST) ctx.ensure_halo(*lcv, Ctx::W_U, NS / 2 + 1);
+    if (lv.N <= 256) launch_tile_cfg<T, NS, MODE, RBGS, 16, 32>(ctx, lv, lcv);
+    else launch_tile_cfg<T, NS, MODE, RBGS, 32, 64>(ctx, lv, lcv);
+    lv.cur ^= 1;
+    lv.hv_u = 0;
+    if (MODE == TILE_PRE) {
+        if (lv.distributed && !lcv->distributed) {
+            comm_allgather_rows(ctx, *lcv, lcv->f);
+            MG_CK(cudaMemsetAsync(lcv->alloc[0], 0, lcv->bytes, ctx.stream));
+        } else if (lcv->distributed) {
+            lcv->hv_f = 0;
+            comm_zero_halo(ctx, *lcv, lcv->u[0]);
+            lcv->hv_u = kHaloRows;
+        }
+    }
+}
+
+static bool use_tile(const Level& lv) { return g_tile && lv.N <= g_tile_maxN; }
+
 static bool stream_ok(const Ctx& ctx, const Level&)
 {
     return (ctx.cfg.flags & MG_FUSED) != 0;
@@ -249,6 +327,16 @@ static void pre_fused(Ctx& ctx, Level& lv, Level& lcv, int nu1)
 {
     const int k = std::min(nu1, 2);
     stream_sweeps<T>(ctx, lv, nu1 - k);
+    if (use_tile(lv)) {
+        if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) {
+            if (k == 2) launch_tile<T, 2, TILE_PRE, false>(ctx, lv, &lcv);
+            else launch_tile<T, 1, TILE_PRE, false>(ctx, lv, &lcv);
+        } else {
+            if (k == 2) launch_tile<T, 4, TILE_PRE, true>(ctx, lv, &lcv);
+            else launch_tile<T, 2, TILE_PRE, true>(ctx, lv, &lcv);
+        }
+        return;
+    }
     if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) {
         if (k == 2) launch_stream<T, 2, MODE_PRE, false>(ctx, lv, &lcv);
         else launch_stream<T, 1, MODE_PRE, false>(ctx, lv, &lcv);
@@ -262,6 +350,17 @@ template <typename T>
 static void post_fused(Ctx& ctx, Level& lv, Level& lcv, int nu2)
 {
     const int k = std::min(nu2, 2);
+    if (use_tile(lv)) {
+        if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) {
+            if (k == 2) launch_tile<T, 2, TILE_POST, false>(ctx, lv, &lcv);
+            else launch_tile<T, 1, TILE_POST, false>(ctx, lv, &lcv);
+        } else {
+            if (k == 2) launch_tile<T, 4, TILE_POST, true>(ctx, lv, &lcv);
+            else launch_tile<T, 2, TILE_POST, true>(ctx, lv, &lcv);
+        }
+        stream_sweeps<T>(ctx, lv, nu2 - k);
+        return;
+    }
     if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) {
         if (k == 2) launch_stream<T, 2, MODE_POST, false>(ctx, lv, &lcv);
         else launch_stream<T, 1, MODE_POST, false>(ctx, lv, &lcv);
