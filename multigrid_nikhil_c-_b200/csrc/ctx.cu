@@ -162,16 +162,33 @@ void Ctx::ensure_halo(Level& lv, Which w, int depth)
     hv = depth;
 }
 
-unsigned long long Ctx::parity_mask() const
+std::string Ctx::state_blob() const
 {
-    unsigned long long m = 0;
-    for (int l = cfg.coarsest_level; l <= cfg.finest_level; ++l)
-        if (levels[l].cur) m |= 1ull << l;
-    return m;
+    std::string b;
+    for (int l = cfg.coarsest_level; l <= cfg.finest_level; ++l) {
+        const Level& lv = levels[l];
+        b.push_back((char)lv.cur);
+        if (lv.distributed) {
+            b.push_back((char)lv.hv_u);
+            b.push_back((char)lv.hv_f);
+            b.push_back((char)lv.hv_r);
+        }
+    }
+    return b;
 }
-void Ctx::set_parity(unsigned long long m)
+
+void Ctx::set_state(const std::string& blob)
 {
-    for (int l = cfg.coarsest_level; l <= cfg.finest_level; ++l) levels[l].cur = (m >> l) & 1;
+    size_t k = 0;
+    for (int l = cfg.coarsest_level; l <= cfg.finest_level; ++l) {
+        Level& lv = levels[l];
+        lv.cur = blob[k++];
+        if (lv.distributed) {
+            lv.hv_u = blob[k++];
+            lv.hv_f = blob[k++];
+            lv.hv_r = blob[k++];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -379,7 +396,7 @@ void Ctx::cycle(int level, int nu1, int nu2, int gamma)
         cycle_rec(level, nu1, nu2, gamma);
         return;
     }
-    auto key = std::make_tuple(level, nu1, nu2, gamma, parity_mask());
+    auto key = std::make_tuple(level, nu1, nu2, gamma, state_blob());
     auto it = graphs.find(key);
     if (it == graphs.end()) {
         fused_pretune(*this, level, nu1, nu2);
@@ -399,7 +416,7 @@ void Ctx::cycle(int level, int nu1, int nu2, int gamma)
         capturing = false;
         MG_CK(cudaStreamEndCapture(stream, &g));
         ge.kernels = lc.n - before;
-        ge.parity_after = parity_mask();
+        ge.state_after = state_blob();
         cudaError_t ie = cudaGraphInstantiate(&ge.exec, g, 0);
         cudaGraphDestroy(g);
         if (ie != cudaSuccess) throw MgError(MG_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
@@ -409,7 +426,7 @@ void Ctx::cycle(int level, int nu1, int nu2, int gamma)
     MG_CK(cudaGraphLaunch(it->second.exec, stream));
     lc.n += it->second.kernels;
     ++graph_launches;
-    set_parity(it->second.parity_after);
+    set_state(it->second.state_after);
 }
 
 void Ctx::fmg(int cycles, int nu1, int nu2)

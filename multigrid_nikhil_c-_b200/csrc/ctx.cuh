@@ -63,7 +63,7 @@ struct Level {
 struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
     long long kernels = 0;
-    unsigned long long parity_after = 0;
+    std::string state_after;   // Ctx::state_blob() once the captured cycle has run
 };
 
 struct Ctx {
@@ -81,7 +81,7 @@ struct Ctx {
     double* d_norm = nullptr;
     double* h_norm = nullptr;  // pinned
     bool capturing = false;
-    std::map<std::tuple<int, int, int, int, unsigned long long>, GraphEntry> graphs;
+    std::map<std::tuple<int, int, int, int, std::string>, GraphEntry> graphs;
     std::map<std::tuple<int, int, int, int>, int> stream_ry;  // tuned chunk height per (level, mode, NS, rbgs)
     Comm* comm = nullptr;
     int aggl_level = 0;  // levels <= aggl_level are replicated on every rank
@@ -117,8 +117,10 @@ struct Ctx {
     void sync();
     void ensure_halo(Level& lv, Which w, int depth);
     void set_halo(Level& lv, Which w, int depth);
-    unsigned long long parity_mask() const;
-    void set_parity(unsigned long long m);
+    // host-side state a captured cycle depends on and changes: which u buffer is current on each level and,
+    // on distributed levels, how many halo rows of u / f / r are valid (decides which exchanges were captured)
+    std::string state_blob() const;
+    void set_state(const std::string& blob);
 
     template <typename T> void smooth_t(int level, int nu);
     template <typename T> double residual_t(int level, bool want_norm, bool store);
