@@ -114,6 +114,13 @@ int mg_host_vcyclemultigrid(mg_ctx* ctx, int level, void* vec_h_inout, const voi
 int mg_host_fullmultigrid(mg_ctx* ctx, const void* f_h, void* vec_h_out, int cycles_per_level,
                           int nu1, int nu2);                                                        /* P:629 */
 
+/* ---- communication-avoiding row-slab schedule (csrc/sched.h; pure host logic, callable without a GPU).
+ *      Fills `ops` with 4 ints per op {kind, level, a, b} (kinds: 0 EXCH a=which(0 u,1 f) b=depth; 1 PRE a=ya b=yb;
+ *      2 POST a=ya b=yb; 3 GATHER_F; 4 REPL_CYCLE) and `halo32` with the halo rows each level must store.
+ *      Returns the number of ops, or -1 when the schedule is not applicable (then the lazy-exchange path runs). ---- */
+int mg_plan_vcycle(int top_level, int agglomerate_level, int world, int rank, int ns_pre, int ns_post,
+                   int valid_halo_u_top, int valid_halo_f_top, int* ops, int max_ops, int* halo32);
+
 /* ---- micro-benchmark hooks used by bench.py (device-timed, CUDA events on the
  *      context's stream; returns milliseconds for `reps` back-to-back launches) ---- */
 int mg_time_op(mg_ctx* ctx, int op, int level, int reps, float* ms_out);

@@ -102,6 +102,7 @@ def lib() -> ctypes.CDLL:
         "mg_host_interpolation2d": (ci, [vp, ci, vp, vp]),
         "mg_host_vcyclemultigrid": (ci, [vp, ci, vp, vp, ci, ci, ci]),
         "mg_host_fullmultigrid": (ci, [vp, vp, vp, ci, ci, ci]),
+        "mg_plan_vcycle": (ci, [ci, ci, ci, ci, ci, ci, ci, ci, ctypes.POINTER(ci), ci, ctypes.POINTER(ci)]),
         "mg_time_op": (ci, [vp, ci, ci, ci, ctypes.POINTER(ctypes.c_float)]),
         "mg_time_cycle": (ci, [vp, ci, ci, ci, ci, ci, ctypes.POINTER(ctypes.c_float)]),
     }

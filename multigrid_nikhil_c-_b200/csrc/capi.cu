@@ -6,6 +6,7 @@
 
 #include "comm.cuh"
 #include "ctx.cuh"
+#include "sched.h"
 
 using namespace mgb;
 
@@ -238,6 +239,23 @@ int mg_host_fullmultigrid(mg_ctx* c, const void* f_h, void* vec_h_out, int cycle
         x.fmg(cycles, nu1, nu2);
         x.get_host(x.cfg.finest_level, Ctx::W_U, vec_h_out);
     });
+}
+
+int mg_plan_vcycle(int top_level, int agglomerate_level, int world, int rank, int ns_pre, int ns_post,
+                   int valid_halo_u_top, int valid_halo_f_top, int* ops, int max_ops, int* halo32)
+{
+    if (top_level < 1 || top_level > 30 || world < 1 || rank < 0 || rank >= world || !ops || !halo32) return -1;
+    const SchedPlan p = sched_plan_vcycle(top_level, agglomerate_level, world, rank, ns_pre, ns_post, valid_halo_u_top,
+                                          valid_halo_f_top);
+    if (!p.ok || (int)p.ops.size() > max_ops) return -1;
+    for (size_t i = 0; i < p.ops.size(); ++i) {
+        ops[4 * i + 0] = p.ops[i].kind;
+        ops[4 * i + 1] = p.ops[i].level;
+        ops[4 * i + 2] = p.ops[i].a;
+        ops[4 * i + 3] = p.ops[i].b;
+    }
+    for (int l = 0; l < 32; ++l) halo32[l] = p.halo[l];
+    return (int)p.ops.size();
 }
 
 int mg_time_op(mg_ctx* c, int op, int level, int reps, float* ms_out)

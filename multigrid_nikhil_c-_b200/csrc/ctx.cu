@@ -8,6 +8,7 @@
 
 #include "comm.cuh"
 #include "fused.cuh"
+#include "sched.h"
 
 namespace mgb {
 
@@ -70,13 +71,33 @@ Ctx::Ctx(const mg_config& c) : cfg(c)
     }
 
     levels.resize(cfg.finest_level + 1);
-    const int halo = kHaloRows;
+    // stored halo rows per level: kHaloRows covers every fused kernel; the communication-avoiding schedule
+    // (opt-in) computes rows beyond the slab and needs deeper halos on the fine levels (sched.h)
+    int halo_rows[32];
+    for (int l = 0; l < 32; ++l) halo_rows[l] = kHaloRows;
+    if (cfg.world > 1) {
+        const char* e = getenv("MGB200_COMM_AVOID");
+        comm_avoid = e && e[0] == '1';
+        if (comm_avoid) {
+            const int ns = (cfg.smoother == MG_SMOOTH_RBGS) ? 4 : 2;
+            int x[32], ex[32], need[32];
+            bool ok = sched_extents(cfg.finest_level, aggl_level, ns, ns, x, ex, need);
+            for (int l = aggl_level + 1; ok && l <= cfg.finest_level; ++l)
+                if (need[l] > ((i64)1 << l) / cfg.world - 1) ok = false;
+            if (ok)
+                for (int l = aggl_level + 1; l <= cfg.finest_level; ++l) halo_rows[l] = std::max(kHaloRows, need[l]);
+            else
+                comm_avoid = false;
+        }
+    }
     for (int l = cfg.coarsest_level; l <= cfg.finest_level; ++l) {
         Level& lv = levels[l];
+        const int halo = halo_rows[l];
         lv.level = l;
         lv.N = 1 << l;
         lv.pitch = round_up((i64)lv.N + 1, 32);
         lv.distributed = (cfg.world > 1 && l > aggl_level);
+        lv.halo = lv.distributed ? halo : 0;
         if (lv.distributed) {
             slab_rows(l, cfg.rank, cfg.world, &lv.own_lo, &lv.own_hi);
             lv.st_lo = std::max(0, lv.own_lo - halo);
@@ -154,7 +175,7 @@ void Ctx::set_halo(Level& lv, Which w, int depth) { halo_ref(lv, w) = depth; }
 void Ctx::ensure_halo(Level& lv, Which w, int depth)
 {
     if (!lv.distributed || depth <= 0) return;
-    MG_REQUIRE(depth <= kHaloRows, "halo depth exceeds the stored halo");
+    MG_REQUIRE(depth <= lv.halo, "halo depth exceeds the stored halo");
     int& hv = halo_ref(lv, w);
     if (hv >= depth) return;
     char* base = (w == W_U) ? lv.u[lv.cur] : (w == W_F ? lv.f : lv.r);
@@ -216,7 +237,7 @@ void Ctx::set_host(int level, Which w, const void* host)
     MG_CK(cudaMemcpy2DAsync(dst, (size_t)lv.pitch * esize, src, (size_t)n * esize, (size_t)n * esize,
                             (size_t)(yb - ya), cudaMemcpyHostToDevice, stream));
     MG_CK(cudaStreamSynchronize(stream));
-    set_halo(lv, w, kHaloRows);
+    set_halo(lv, w, lv.halo);
 }
 
 void Ctx::get_host(int level, Which w, void* host)
@@ -236,7 +257,7 @@ void Ctx::zero_u(int level)
 {
     Level& lv = L(level);
     MG_CK(cudaMemsetAsync(lv.alloc[lv.cur], 0, lv.bytes, stream));
-    lv.hv_u = kHaloRows;
+    lv.hv_u = lv.halo;
 }
 
 void Ctx::force_constant(double fval)
@@ -248,7 +269,7 @@ void Ctx::force_constant(double fval)
     if (f64()) launch_fill<double>(stream, lc, (double*)lv.f, lv.pitch, lv.N, ya, yb, b);
     else launch_fill<float>(stream, lc, (float*)lv.f, lv.pitch, lv.N, ya, yb, (float)b);
     MG_CK(cudaGetLastError());
-    lv.hv_f = kHaloRows;
+    lv.hv_f = lv.halo;
 }
 
 // ---------------------------------------------------------------------------------
@@ -336,7 +357,7 @@ void Ctx::restrict_t(int fine_level, bool from_rhs)
     lcv.hv_f = 0;
     if (lcv.distributed && !from_rhs) {
         comm_zero_halo(*this, lcv, lcv.u[lcv.cur]);   // halo rows of the zero guess
-        lcv.hv_u = kHaloRows;
+        lcv.hv_u = lcv.halo;
     }
 }
 

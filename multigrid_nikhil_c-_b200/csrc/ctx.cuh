@@ -49,6 +49,7 @@ struct Level {
     bool distributed = false;
     int own_lo = 0, own_hi = 0;  // owned interior node rows [own_lo, own_hi)
     int st_lo = 0, st_hi = 0;    // stored node rows [st_lo, st_hi) (owned + halo / ring)
+    int halo = 0;                // halo rows stored per side on a distributed level (kHaloRows, or more for MGB200_COMM_AVOID)
     size_t bytes = 0;            // bytes of one array
     void* alloc[4] = {nullptr, nullptr, nullptr, nullptr};  // u0, u1, f, r (real allocations)
     char* u[2] = {nullptr, nullptr};                         // virtual row-0 bases
@@ -86,6 +87,7 @@ struct Ctx {
     Comm* comm = nullptr;
     int aggl_level = 0;  // levels <= aggl_level are replicated on every rank
     bool graph_dist = false;  // capture NCCL exchanges into cycle graphs (MGB200_GRAPH_DIST=1)
+    bool comm_avoid = false;  // communication-avoiding slab schedule (MGB200_COMM_AVOID=1, csrc/sched.h)
 
     explicit Ctx(const mg_config& c);
     ~Ctx();

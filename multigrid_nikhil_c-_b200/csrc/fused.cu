@@ -8,6 +8,7 @@
 #include <cstdlib>
 
 #include "comm.cuh"
+#include "sched.h"
 #include "stream.cuh"
 #include "tail.cuh"
 #include "tile.cuh"
@@ -83,7 +84,7 @@ static int default_ry(const Level& lv, int strips)
 }
 
 template <typename T, int NS, int MODE>
-static StreamArgs<T> make_args(Ctx& ctx, Level& lv, Level* lcv, int ry)
+static StreamArgs<T> make_args(Ctx& ctx, Level& lv, Level* lcv, int ry, int ya = -1, int yb = -1)
 {
     typedef StreamCfg<T, NS, MODE> C;
     StreamArgs<T> a;
@@ -92,8 +93,8 @@ static StreamArgs<T> make_args(Ctx& ctx, Level& lv, Level* lcv, int ry)
     a.f = (const T*)lv.f;
     a.pitch = lv.pitch;
     a.N = lv.N;
-    a.ya = lv.own_lo;
-    a.yb = lv.own_hi;
+    a.ya = (ya >= 0) ? ya : lv.own_lo;
+    a.yb = (yb >= 0) ? yb : lv.own_hi;
     a.row_lo = lv.st_lo;
     a.row_hi = lv.st_hi;
     const int rows = a.yb - a.ya;
@@ -213,7 +214,7 @@ static void launch_stream(Ctx& ctx, Level& lv, Level* lcv)
         } else if (lcv->distributed) {
             lcv->hv_f = 0;
             comm_zero_halo(ctx, *lcv, lcv->u[0]);
-            lcv->hv_u = kHaloRows;
+            lcv->hv_u = lcv->halo;
         }
     }
 }
@@ -284,7 +285,7 @@ static void launch_tile(Ctx& ctx, Level& lv, Level* lcv)
         } else if (lcv->distributed) {
             lcv->hv_f = 0;
             comm_zero_halo(ctx, *lcv, lcv->u[0]);
-            lcv->hv_u = kHaloRows;
+            lcv->hv_u = lcv->halo;
         }
     }
 }
@@ -407,8 +408,92 @@ static void run_tail(Ctx& ctx, int level, int nu1, int nu2, int gamma)
     MG_CK(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------
+// communication-avoiding V-cycle over the distributed levels (sched.h), opt-in MGB200_COMM_AVOID=1.
+// The op list comes from the same planner the CPU emulation test executes with the oracle.
+// ---------------------------------------------------------------------------------
+template <typename T, int NS, int MODE, bool RBGS>
+static void launch_stream_range(Ctx& ctx, Level& lv, Level* lcv, int ya, int yb)
+{
+    if (MODE == MODE_PRE) lcv->cur = 0;
+    const int ry = tuned_ry<T, NS, MODE, RBGS>(ctx, lv, lcv);
+    const StreamArgs<T> a = make_args<T, NS, MODE>(ctx, lv, lcv, ry, ya, yb);
+    raw_launch<T, NS, MODE, RBGS>(ctx, a);
+    lv.cur ^= 1;
+}
+
+template <typename T>
+static void comm_avoid_run(Ctx& ctx, const SchedPlan& plan, int nu1, int nu2)
+{
+    const bool rb = ctx.cfg.smoother == MG_SMOOTH_RBGS;
+    for (const SchedOp& op : plan.ops) {
+        Level& lv = ctx.L(op.level);
+        switch (op.kind) {
+            case SCHED_EXCH: {
+                comm_halo_exchange(ctx, lv, op.a == 0 ? lv.u[lv.cur] : lv.f, op.b);
+                if (op.a == 0) lv.hv_u = op.b; else lv.hv_f = op.b;
+                break;
+            }
+            case SCHED_PRE: {
+                Level& lcv = ctx.L(op.level - 1);
+                if (lcv.distributed) comm_zero_halo(ctx, lcv, lcv.u[0]);   // rows of the zero guess the kernel does not reach
+                if (!rb) {
+                    if (nu1 == 2) launch_stream_range<T, 2, MODE_PRE, false>(ctx, lv, &lcv, op.a, op.b);
+                    else launch_stream_range<T, 1, MODE_PRE, false>(ctx, lv, &lcv, op.a, op.b);
+                } else {
+                    if (nu1 == 2) launch_stream_range<T, 4, MODE_PRE, true>(ctx, lv, &lcv, op.a, op.b);
+                    else launch_stream_range<T, 2, MODE_PRE, true>(ctx, lv, &lcv, op.a, op.b);
+                }
+                lv.hv_u = plan.e[op.level];
+                if (lcv.distributed) {
+                    lcv.hv_f = plan.e[op.level] / 2;
+                    lcv.hv_u = lcv.halo;
+                }
+                break;
+            }
+            case SCHED_GATHER_F: {
+                comm_allgather_rows(ctx, lv, lv.f);
+                lv.cur = 0;
+                MG_CK(cudaMemsetAsync(lv.alloc[0], 0, lv.bytes, ctx.stream));
+                break;
+            }
+            case SCHED_REPL_CYCLE: ctx.cycle_rec(op.level, nu1, nu2, 1); break;
+            case SCHED_POST: {
+                Level& lcv = ctx.L(op.level - 1);
+                if (!rb) {
+                    if (nu2 == 2) launch_stream_range<T, 2, MODE_POST, false>(ctx, lv, &lcv, op.a, op.b);
+                    else launch_stream_range<T, 1, MODE_POST, false>(ctx, lv, &lcv, op.a, op.b);
+                } else {
+                    if (nu2 == 2) launch_stream_range<T, 4, MODE_POST, true>(ctx, lv, &lcv, op.a, op.b);
+                    else launch_stream_range<T, 2, MODE_POST, true>(ctx, lv, &lcv, op.a, op.b);
+                }
+                lv.hv_u = plan.x[op.level];
+                break;
+            }
+        }
+    }
+}
+
+static bool comm_avoid_cycle(Ctx& ctx, int level, int nu1, int nu2, int gamma)
+{
+    if (!ctx.comm_avoid || ctx.cfg.world < 2 || gamma != 1 || !(ctx.cfg.flags & MG_FUSED)) return false;
+    if (nu1 < 1 || nu1 > 2 || nu2 < 1 || nu2 > 2) return false;
+    Level& lv = ctx.L(level);
+    if (!lv.distributed || ctx.aggl_level < ctx.cfg.coarsest_level) return false;
+    const bool rb = ctx.cfg.smoother == MG_SMOOTH_RBGS;
+    const int ns1 = rb ? 2 * nu1 : nu1, ns2 = rb ? 2 * nu2 : nu2;
+    const SchedPlan plan = sched_plan_vcycle(level, ctx.aggl_level, ctx.cfg.world, ctx.cfg.rank, ns1, ns2, lv.hv_u, lv.hv_f);
+    if (!plan.ok) return false;
+    for (int l = ctx.aggl_level + 1; l <= level; ++l)
+        if (plan.halo[l] > ctx.L(l).halo) return false;
+    if (ctx.f64()) comm_avoid_run<double>(ctx, plan, nu1, nu2);
+    else comm_avoid_run<float>(ctx, plan, nu1, nu2);
+    return true;
+}
+
 bool fused_cycle_level(Ctx& ctx, int level, int nu1, int nu2, int gamma)
 {
+    if (comm_avoid_cycle(ctx, level, nu1, nu2, gamma)) return true;
     if (level == tail_top(ctx)) {
         if (ctx.f64()) run_tail<double>(ctx, level, nu1, nu2, gamma);
         else run_tail<float>(ctx, level, nu1, nu2, gamma);
