@@ -375,6 +375,72 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_micro(args, rank, world, local_rank):
+    """BASELINE.json configs[4]: smoother + residual sweep alone (HBM-roofline micro-benchmark) with temporal
+    blocking depths k = 1, 2, 3, 4, on one GPU or on row slabs.  Resident data only (b = f h^2, u = 0), no host
+    vectors; prints one JSON line: bytes are the algorithmic 3S per point per LAUNCH, so the
+    "effective" rate of a k-sweep launch is k times its GB/s."""
+    import torch
+    import mgb200
+    from mgb200 import capi
+    torch.cuda.set_device(local_rank)
+    dist, comm = None, None
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        blob = [mgb200.comm_id() if rank == 0 else None]
+        dist.broadcast_object_list(blob, src=0)
+        comm = blob[0]
+    level = args.level or 15
+    dtype = np.float32 if args.dtype == "f32" else np.float64
+    esize = np.dtype(dtype).itemsize
+    n = (1 << level) - 1
+    mg = mgb200.Multigrid(level, coarsest_level=max(1, level - 1), dtype=dtype, smoother=args.smoother, device=local_rank,
+                          rank=rank, world=world, comm_id=comm, agglomerate_level=args.aggl or max(1, level - 1))
+    mg.force_constant(4.0)
+    mg.zero_u(level)
+    rows = n if world == 1 else mg.info(capi.MG_INFO_ROW_END, level) - mg.info(capi.MG_INFO_ROW_BEGIN, level)
+    pts_total = n * n
+    peak, peak_src = measured_peak_gbs()
+    reps = max(3, args.steps)
+    out = {}
+    ops = [("jacobi_k1", capi.MG_OP_SMOOTH1, 1, 3.0), ("jacobi_k2_one_launch", capi.MG_OP_SMOOTH2, 2, 3.0),
+           ("jacobi_k3_one_launch", capi.MG_OP_SMOOTH3, 3, 3.0), ("jacobi_k4_one_launch", capi.MG_OP_SMOOTH4, 4, 3.0),
+           ("residual", capi.MG_OP_RESIDUAL, 1, 3.0), ("residual_norm_only", capi.MG_OP_RESIDUAL_NORM, 1, 2.0)]
+    for name, op, k, s_per_pt in ops:
+        try:
+            mg.time_op(op, level, max(1, args.warmup))
+            if dist is not None:
+                dist.barrier()
+            ms = mg.time_op(op, level, reps) / reps
+        except capi.MgError:
+            continue
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        gbs = s_per_pt * esize * pts_total / (ms * 1e-3) / 1e9          # whole job (all ranks)
+        out[name] = {"ms": ms, "sweeps_per_launch": k, "GBps": gbs, "frac_of_peak_per_gpu": gbs / world / peak,
+                     "effective_GBps_per_sweep": gbs * k, "point_updates_per_s": k * pts_total / (ms * 1e-3)}
+    best = max(out.items(), key=lambda kv: kv[1].get("point_updates_per_s", 0))
+    line = {"metric": "smoother_point_updates_per_s", "value": best[1]["point_updates_per_s"], "unit": UNIT, "n_gpus": world,
+            "steps": reps, "warmup": args.warmup, "ms_per_step": best[1]["ms"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"{n + 2}^2 {'fp32' if esize == 4 else 'fp64'} smoother + residual sweeps alone "
+                                   f"(temporal blocking k=1..4), {args.smoother}" + ("" if world == 1 else f", row slabs over {world} GPUs"),
+                       "level": level, "rows_per_rank": rows, "best": best[0]},
+            "roofline": {"bound": "hbm", "achieved": best[1]["GBps"] / world, "peak": peak, "unit": "GB/s",
+                         "frac": best[1]["GBps"] / world / peak, "traffic": None, "peak_source": peak_src, "kernels": out},
+            "gpu_launches": int(mg.launches)}
+    mg.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -393,6 +459,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--aggl", type=int, default=0, help="agglomeration level for N>1 (0 = library default)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (tuning runs)")
+    ap.add_argument("--micro", action="store_true",
+                    help="BASELINE configs[4]: smoother/residual micro-benchmark (default 32769^2; use --dtype f32)")
     ap.add_argument("--full-host-vectors", action="store_true",
                     help="N>1: every rank holds the full-grid host vectors (default: only the rows of its slab)")
     args = ap.parse_args()
@@ -401,6 +469,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.micro:
+        run_micro(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

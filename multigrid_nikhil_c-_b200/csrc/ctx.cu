@@ -491,6 +491,10 @@ float Ctx::time_op(int op, int level, int reps)
         switch (op) {
             case MG_OP_SMOOTH1: smooth(level, 1); break;
             case MG_OP_SMOOTH2: smooth(level, 2); break;
+            case MG_OP_SMOOTH3: smooth(level, 3); break;
+            case MG_OP_SMOOTH4:
+                if (!fused_time_sweeps4(*this, level)) throw MgError(MG_ERR_STATE, "4-sweep temporally blocked kernel not available for this config");
+                break;
             case MG_OP_RESIDUAL: residual(level, false, true); break;
             case MG_OP_RESIDUAL_NORM: {
                 Level& lv = L(level);

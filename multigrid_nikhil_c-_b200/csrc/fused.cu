@@ -37,6 +37,7 @@ static void set_attrs_t()
     set_attr<T, 1, MODE_SWEEPS, false>();
     set_attr<T, 2, MODE_SWEEPS, false>();
     set_attr<T, 3, MODE_SWEEPS, false>();
+    set_attr<T, 4, MODE_SWEEPS, false>();
     set_attr<T, 1, MODE_PRE, false>();
     set_attr<T, 2, MODE_PRE, false>();
     set_attr<T, 1, MODE_POST, false>();
@@ -541,6 +542,15 @@ void fused_pretune(Ctx& ctx, int level, int nu1, int nu2)
     if (!(ctx.cfg.flags & MG_FUSED) || nu1 < 1 || nu2 < 1) return;
     if (ctx.f64()) pretune_t<double>(ctx, level, nu1, nu2);
     else pretune_t<float>(ctx, level, nu1, nu2);
+}
+
+bool fused_time_sweeps4(Ctx& ctx, int level)
+{
+    Level& lv = ctx.L(level);
+    if (!stream_ok(ctx, lv) || ctx.cfg.smoother != MG_SMOOTH_JACOBI) return false;
+    if (ctx.f64()) launch_stream<double, 4, MODE_SWEEPS, false>(ctx, lv, nullptr);
+    else launch_stream<float, 4, MODE_SWEEPS, false>(ctx, lv, nullptr);
+    return true;
 }
 
 bool fused_time_hook(Ctx& ctx, int level, bool pre)

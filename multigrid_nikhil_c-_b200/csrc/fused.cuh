@@ -15,5 +15,7 @@ bool fused_cycle_level(Ctx& ctx, int level, int nu1, int nu2, int gamma);
 void fused_pretune(Ctx& ctx, int level, int nu1, int nu2);
 // one launch of the fused pre- (true) or post-smoothing (false) kernel for timing; false if unavailable
 bool fused_time_hook(Ctx& ctx, int level, bool pre);
+// micro-benchmark only: four weighted-Jacobi sweeps temporally blocked in one launch (not used by the cycles)
+bool fused_time_sweeps4(Ctx& ctx, int level);
 
 }  // namespace mgb

@@ -47,6 +47,9 @@ class StubMG:
     def zero_u(self, level):
         pass
 
+    def force_constant(self, f):
+        pass
+
     def time_cycle(self, level, nu1, nu2, gamma, reps):
         self._launches += 13 * reps
         return 0.3 * reps * 4.0 ** (level - 12)
@@ -70,7 +73,8 @@ class StubMG:
 
 def _args(**kw):
     d = dict(gpus=1, steps=3, warmup=1, impl="ours", level=6, dtype="f64", smoother="jacobi", nu1=2, nu2=2, gamma=1,
-             no_graph=False, no_fused=False, no_tail=False, no_cpu=True, aggl=0, no_e2e=False, full_host_vectors=False)
+             no_graph=False, no_fused=False, no_tail=False, no_cpu=True, aggl=0, no_e2e=False, full_host_vectors=False,
+             micro=False)
     d.update(kw)
     return argparse.Namespace(**d)
 
@@ -124,3 +128,14 @@ def test_reference_arm_line(capsys):
     assert d["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
     bench.run_reference(_args(impl="reference", level=6), rank=1, world=2)    # other ranks print nothing
     assert capsys.readouterr().out == ""
+
+
+def test_micro_benchmark_line(monkeypatch, capsys):
+    import torch
+    import mgb200
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(mgb200, "Multigrid", lambda level, **kw: StubMG(level, dtype=kw.get("dtype", np.float64)))
+    bench.run_micro(_args(micro=True, level=9, dtype="f32", steps=3), rank=0, world=1, local_rank=0)
+    d = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert d["metric"] == "smoother_point_updates_per_s" and d["dtype"] == "f32"
+    assert "jacobi_k2_one_launch" in d["roofline"]["kernels"] and d["roofline"]["frac"] > 0
