@@ -20,7 +20,8 @@ EXCH, PRE, POST, GATHER_F, REPL_CYCLE = range(5)
 
 
 class TraceEmu:
-    def __init__(self, lib, orc, top, aggl, rank, world, ns1, ns2, halos):
+    def __init__(self, lib, orc, top, aggl, rank, world, ns1, ns2, halos, rbgs=False):
+        self.rbgs = rbgs
         self.lib, self.o, self.top, self.aggl, self.rank, self.world = lib, orc, top, aggl, rank, world
         self.ns1, self.ns2, self.halo = ns1, ns2, halos
         self.u, self.f, self.own = {}, {}, {}
@@ -71,13 +72,17 @@ class TraceEmu:
             arr[row:row + t.shape[0]] = t.numpy()
         self.exchanges += 1
 
+    def smooth(self, u, f, ns):
+        """ns pipeline stages: ns Jacobi sweeps, or ns/2 red-black sweeps (one stage per colour)"""
+        return self.o.rbgs(u, f, ns // 2) if self.rbgs else self.o.jacobirelaxation(u, f, ns)
+
     def run(self, ops):
         o = self.o
         for kind, l, a, b in ops:
             if kind == EXCH:
                 self.exchange(l, self.u[l] if a == 0 else self.f[l], b)
             elif kind == PRE:
-                u1 = o.jacobirelaxation(self.u[l].reshape(-1), self.f[l].reshape(-1), self.ns1)
+                u1 = self.smooth(self.u[l].reshape(-1), self.f[l].reshape(-1), self.ns1)
                 r = o.residual(u1, self.f[l].reshape(-1))
                 coarse = o.restriction2d(r)
                 self.u[l] = self.keep(l, u1, (a, b))
@@ -97,16 +102,16 @@ class TraceEmu:
                 self.u[l] = np.zeros_like(self.f[l])
             elif kind == REPL_CYCLE:
                 import oracle
-                p = oracle.Params(nu1=self.ns1, nu2=self.ns2)
+                p = oracle.Params(nu1=self.ns1 // 2, nu2=self.ns2 // 2, smoother=1) if self.rbgs else oracle.Params(nu1=self.ns1, nu2=self.ns2)
                 self.u[l] = o.vcyclemultigrid(self.u[l].reshape(-1), self.f[l].reshape(-1), p).reshape(self.n(l), self.n(l))
             elif kind == POST:
                 e = self.u[l - 1].reshape(-1)
                 u0 = o.prolong_correct(e, self.u[l].reshape(-1))
-                u2 = o.jacobirelaxation(u0, self.f[l].reshape(-1), self.ns2)
+                u2 = self.smooth(u0, self.f[l].reshape(-1), self.ns2)
                 self.u[l] = self.keep(l, u2, (a, b))
 
 
-def _worker(rank, world, port, top, aggl, ns1, ns2, q):
+def _worker(rank, world, port, top, aggl, ns1, ns2, q, rbgs=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -124,14 +129,15 @@ def _worker(rank, world, port, top, aggl, ns1, ns2, q):
         assert nops > 0, "plan not applicable"
         plan = [tuple(ops[4 * i:4 * i + 4]) for i in range(nops)]
         assert sum(1 for k in plan if k[0] == EXCH) == 1 and sum(1 for k in plan if k[0] == GATHER_F) == 1
-        emu = TraceEmu(lib, o, top, aggl, rank, world, ns1, ns2, list(halo))
+        emu = TraceEmu(lib, o, top, aggl, rank, world, ns1, ns2, list(halo), rbgs)
         x, b = rand_vec(top, np.float64, 71), rand_vec(top, np.float64, 72, 1e-3)
         n = emu.n(top)
         # the rank holds only its owned rows of u (halo invalid: hv_u = 0) and f on all stored rows
         emu.u[top] = emu.keep(top, x, emu.own[top])
         emu.f[top] = emu.keep(top, b, emu.stored(top))
         emu.run(plan)
-        want = o.vcyclemultigrid(x, b, oracle.Params(nu1=ns1, nu2=ns2)).reshape(n, n)
+        pp = oracle.Params(nu1=ns1 // 2, nu2=ns2 // 2, smoother=1) if rbgs else oracle.Params(nu1=ns1, nu2=ns2)
+        want = o.vcyclemultigrid(x, b, pp).reshape(n, n)
         a, bb = emu.own[top]
         got = emu.u[top][a - 1:bb - 1]
         assert not np.isnan(got).any(), "owned rows depend on rows the schedule did not provide"
@@ -144,13 +150,14 @@ def _worker(rank, world, port, top, aggl, ns1, ns2, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,top,aggl,ns1,ns2", [(2, 8, 5, 2, 2), (2, 9, 6, 2, 2), (4, 9, 6, 2, 2), (2, 8, 6, 1, 1),
-                                                   (4, 9, 7, 2, 1), (2, 9, 5, 1, 2)])
-def test_comm_avoiding_schedule_is_sufficient(world, top, aggl, ns1, ns2):
+@pytest.mark.parametrize("world,top,aggl,ns1,ns2,rbgs", [(2, 8, 5, 2, 2, False), (2, 9, 6, 2, 2, False), (4, 9, 6, 2, 2, False),
+                                                        (2, 8, 6, 1, 1, False), (4, 9, 7, 2, 1, False), (2, 9, 5, 1, 2, False),
+                                                        (2, 9, 7, 4, 4, True), (2, 9, 6, 2, 2, True)])
+def test_comm_avoiding_schedule_is_sufficient(world, top, aggl, ns1, ns2, rbgs):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + world * 10 + top + aggl + ns1 * 3 + ns2
-    procs = [ctx.Process(target=_worker, args=(r, world, port, top, aggl, ns1, ns2, q)) for r in range(world)]
+    port = 29700 + world * 10 + top + aggl + ns1 * 3 + ns2 + (50 if rbgs else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, top, aggl, ns1, ns2, q, rbgs)) for r in range(world)]
     for pr in procs:
         pr.start()
     res = [q.get(timeout=300) for _ in procs]
