@@ -351,6 +351,21 @@ def run_ours(args, rank, world, local_rank):
            "d2h_bytes_per_step": rows * n * esize,
            "call": "mg_host_vcyclemultigrid (vcyclemultigrid P:575 on pinned host vectors)"}
 
+    # informational: the reference's top-level call shape, fullmultigrid(f_h) -> u (P:629 / main P:727): one H2D of f,
+    # one V(2,2) per level on the way up, one D2H of u.  Transfers are amortised over ~4/3 cycles' worth of work.
+    if world == 1 and not args.no_e2e:
+        try:
+            fmg_upd = sum(updates_per_cycle(l, 1, nu1, nu2) for l in range(1, level + 1))
+            mg.fullmultigrid(f_host, 1, nu1, nu2)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                mg.fullmultigrid(f_host, 1, nu1, nu2)
+            fmg_ms = (time.perf_counter() - t0) * 1e3 / 3
+            e2e["fullmultigrid_call"] = {"ms": fmg_ms, "value": fmg_upd / (fmg_ms * 1e-3), "unit": UNIT,
+                                         "call": "mg_host_fullmultigrid, 1 V(2,2) per level, host f in / host u out (allocates the result)"}
+        except Exception as ex:  # noqa: BLE001 - informational leg only
+            e2e["fullmultigrid_call"] = {"error": str(ex)}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if dtype == np.float64 else "f32", "data": "synthetic",
