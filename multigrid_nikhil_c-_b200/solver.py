@@ -277,10 +277,13 @@ class Multigrid:
                                                    nu1, nu2, gamma))
         return out
 
-    def fullmultigrid(self, f_h, cycles_per_level: int = 1, nu1: int = 2, nu2: int = 2) -> np.ndarray:
-        """P:629-650 (reference: cycles_per_level = mu0+1 = 31, nu1 = nu2 = 10)."""
+    def fullmultigrid(self, f_h, cycles_per_level: int = 1, nu1: int = 2, nu2: int = 2, out=None) -> np.ndarray:
+        """P:629-650 (reference: cycles_per_level = mu0+1 = 31, nu1 = nu2 = 10).  `out`: optional result buffer."""
         level = self.finest_level
-        out = np.zeros(self.side(level) ** 2, dtype=self.dtype)
+        if out is None:
+            out = np.zeros(self.side(level) ** 2, dtype=self.dtype)
+        elif out.dtype != self.dtype or out.size != self.side(level) ** 2 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous array of the context dtype and finest-level size")
         self._ck(self._lib.mg_host_fullmultigrid(self._ctx, _vp(self._vec(level, f_h)), _vp(out),
                                                  cycles_per_level, nu1, nu2))
         return out

@@ -64,8 +64,8 @@ class StubMG:
         assert inplace and u.size == f.size
         return u
 
-    def fullmultigrid(self, f, cycles, nu1, nu2):
-        return np.zeros_like(f)
+    def fullmultigrid(self, f, cycles, nu1, nu2, out=None):
+        return out if out is not None else np.zeros_like(f)
 
     def vcyclemultigrid_slab(self, level, u, f, nu1, nu2, gamma):
         assert u.size == f.size
