@@ -1,0 +1,87 @@
+"""GPU parity tests of the OPT-IN code paths (written in round 1 after the GPU budget was spent, CPU-verified
+only): shared-memory tile kernels (MGB200_TILE=1) and, under torchrun via tests/mgpu_worker.py, the
+communication-avoiding slab schedule (MGB200_COMM_AVOID=1) and distributed graph capture (MGB200_GRAPH_DIST=1).
+
+They are skipped unless MGB200_TEST_OPTIN=1, so that an unverified path can never turn the default GPU suite red:
+    MGB200_TEST_OPTIN=1 python -m pytest tests/test_optin_gpu.py -m gpu -x -q
+The knobs are read from the environment when a context is created, so they are toggled in-process."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import assert_bitwise, rand_vec
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("MGB200_TEST_OPTIN") != "1", reason="opt-in paths: set MGB200_TEST_OPTIN=1")]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture
+def knob():
+    saved = {}
+
+    def set_knob(name, value):
+        saved.setdefault(name, os.environ.get(name))
+        os.environ[name] = value
+    yield set_knob
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("smoother,nu1,nu2,gamma", [("jacobi", 2, 2, 1), ("jacobi", 1, 1, 1), ("jacobi", 2, 1, 2),
+                                                    ("rbgs", 2, 2, 1), ("rbgs", 1, 1, 2), ("jacobi", 4, 3, 1)])
+@pytest.mark.parametrize("level", [3, 5, 7, 8, 10])
+def test_tile_kernels_cycles_bitwise(mgb, orc, knob, level, dtype, smoother, nu1, nu2, gamma):
+    knob("MGB200_TILE", "1")
+    x, b = rand_vec(level, dtype, 81), rand_vec(level, dtype, 82, 1e-3)
+    p = oracle.Params(nu1=nu1, nu2=nu2, gamma=gamma, smoother=1 if smoother == "rbgs" else 0, nthreads=4)
+    want = [x]
+    for _ in range(3):
+        want.append(orc.vcyclemultigrid(want[-1], b, p))
+    for graph, tail in ((False, False), (True, True)):
+        with mgb.Multigrid(level, dtype=dtype, smoother=smoother, graph=graph, fused=True, coarse_tail=tail) as mg:
+            mg.set_u(level, x)
+            mg.set_rhs(level, b)
+            for k in range(3):
+                mg.cycle(level, nu1, nu2, gamma)
+                assert_bitwise(mg.get_u(level), want[k + 1], f"tile cycle {k + 1} graph={graph} tail={tail}")
+
+
+def test_tile_kernels_full_size_and_speed(mgb, orc, knob):
+    """4097^2: the tile kernels take over levels <= 10; result must not change, cycle must not get slower."""
+    level = 12
+    n = (1 << level) - 1
+    b = (1.0 / 4096.0) ** 2 * np.random.default_rng(1234).uniform(-1, 1, n * n)
+    want = orc.vcyclemultigrid(np.zeros(n * n), b, oracle.Params(nthreads=orc.max_threads()))
+    times = {}
+    for tile in ("0", "1"):
+        knob("MGB200_TILE", tile)
+        with mgb.Multigrid(level) as mg:
+            mg.set_rhs(level, b)
+            mg.zero_u(level)
+            mg.cycle(level, 2, 2, 1)
+            assert_bitwise(mg.get_u(level), want, f"V(2,2) at 4097^2, MGB200_TILE={tile}")
+            mg.time_cycle(level, 2, 2, 1, 5)
+            times[tile] = mg.time_cycle(level, 2, 2, 1, 20) / 20
+    print(f"V(2,2) 4097^2: stream-only {times['0'] * 1e3:.1f} us, with tile kernels {times['1'] * 1e3:.1f} us")
+    assert times["1"] < 1.05 * times["0"]
+
+
+@pytest.mark.parametrize("env", [{"MGB200_COMM_AVOID": "1"}, {"MGB200_GRAPH_DIST": "1"},
+                                 {"MGB200_COMM_AVOID": "1", "MGB200_GRAPH_DIST": "1"}, {"MGB200_TILE": "1"}])
+def test_multigpu_optin_paths(env):
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900, env={**os.environ, **env})
+    assert out.returncode == 0 and "MGPU OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
