@@ -137,6 +137,10 @@ Ctx::Ctx(const mg_config& c) : cfg(c)
         const char* e = getenv("MGB200_GRAPH_DIST");
         graph_dist = e && e[0] == '1';
     }
+    {
+        const char* zg = getenv("MGB200_ZERO_GUESS");
+        zero_guess = zg && zg[0] == '1';
+    }
     fused_setup(*this);
     MG_CK(cudaStreamSynchronize(stream));
 }
@@ -167,6 +171,15 @@ const Level& Ctx::L(int level) const { return const_cast<Ctx*>(this)->L(level); 
 
 void Ctx::sync() { MG_CK(cudaStreamSynchronize(stream)); }
 
+// write the zeros of a logically-zero iterate (no-op unless MGB200_ZERO_GUESS left one pending)
+void Ctx::materialize_u(Level& lv)
+{
+    if (!lv.u_zero) return;
+    MG_CK(cudaMemsetAsync(lv.alloc[lv.cur], 0, lv.bytes, stream));
+    lv.u_zero = false;
+    lv.hv_u = lv.halo;
+}
+
 static int& halo_ref(Level& lv, Ctx::Which w) { return w == Ctx::W_U ? lv.hv_u : (w == Ctx::W_F ? lv.hv_f : lv.hv_r); }
 
 void Ctx::set_halo(Level& lv, Which w, int depth) { halo_ref(lv, w) = depth; }
@@ -188,7 +201,7 @@ std::string Ctx::state_blob() const
     std::string b;
     for (int l = cfg.coarsest_level; l <= cfg.finest_level; ++l) {
         const Level& lv = levels[l];
-        b.push_back((char)lv.cur);
+        b.push_back((char)(lv.cur | (lv.u_zero ? 2 : 0)));
         if (lv.distributed) {
             b.push_back((char)lv.hv_u);
             b.push_back((char)lv.hv_f);
@@ -203,7 +216,9 @@ void Ctx::set_state(const std::string& blob)
     size_t k = 0;
     for (int l = cfg.coarsest_level; l <= cfg.finest_level; ++l) {
         Level& lv = levels[l];
-        lv.cur = blob[k++];
+        lv.cur = blob[k] & 1;
+        lv.u_zero = (blob[k] & 2) != 0;
+        ++k;
         if (lv.distributed) {
             lv.hv_u = blob[k++];
             lv.hv_f = blob[k++];
@@ -230,6 +245,7 @@ void Ctx::set_host(int level, Which w, const void* host)
 {
     MG_REQUIRE(host != nullptr, "null host pointer");
     Level& lv = L(level);
+    if (w == W_U) lv.u_zero = false;   // overwritten below (ring rows / columns of every buffer are zero already)
     const i64 n = lv.N - 1;
     const int ya = std::max(lv.st_lo, 1), yb = std::min(lv.st_hi, lv.N);
     char* dst = which_ptr(lv, w) + ((i64)ya * lv.pitch + 1) * esize;
@@ -244,6 +260,7 @@ void Ctx::get_host(int level, Which w, void* host)
 {
     MG_REQUIRE(host != nullptr, "null host pointer");
     Level& lv = L(level);
+    if (w == W_U) materialize_u(lv);
     const i64 n = lv.N - 1;
     const int ya = lv.own_lo, yb = lv.own_hi;
     const char* src = which_ptr(lv, w) + ((i64)ya * lv.pitch + 1) * esize;
@@ -258,6 +275,7 @@ void Ctx::zero_u(int level)
     Level& lv = L(level);
     MG_CK(cudaMemsetAsync(lv.alloc[lv.cur], 0, lv.bytes, stream));
     lv.hv_u = lv.halo;
+    lv.u_zero = false;
 }
 
 void Ctx::force_constant(double fval)
@@ -280,6 +298,7 @@ void Ctx::smooth_t(int level, int nu)
 {
     Level& lv = L(level);
     if (nu <= 0) return;
+    materialize_u(lv);
     if (cfg.smoother == MG_SMOOTH_JACOBI) {
         // constants exactly as the oracle forms them (P:127, P:138-140)
         const T om = (T)cfg.omega;
@@ -312,6 +331,7 @@ template <typename T>
 double Ctx::residual_t(int level, bool want_norm, bool store)
 {
     Level& lv = L(level);
+    materialize_u(lv);
     ensure_halo(lv, W_U, 1);
     if (store) lv.hv_r = 0;
     const int np = launch_residual<T>(stream, lc, (const T*)lv.u[lv.cur], (const T*)lv.f, (T*)lv.r, lv.pitch,
@@ -340,7 +360,10 @@ void Ctx::restrict_t(int fine_level, bool from_rhs)
     const T w = (T)cfg.restrict_weight;
     const T* src = (const T*)(from_rhs ? lf.f : lf.r);
     ensure_halo(lf, from_rhs ? W_F : W_R, 1);   // edge row of the neighbour's r (or f)
-    if (!from_rhs) lcv.cur = 0;                  // fixed buffer for the zero guess keeps graph replays valid
+    if (!from_rhs) {
+        lcv.cur = 0;                             // fixed buffer for the zero guess keeps graph replays valid
+        lcv.u_zero = false;                      // real zeros are written below
+    }
     if (lf.distributed && !lcv.distributed) {
         // agglomeration: every rank restricts its slab of coarse rows, then all-gathers
         int lo, hi;
@@ -366,6 +389,8 @@ void Ctx::prolong_t(int fine_level, bool add)
 {
     Level& lf = L(fine_level);
     Level& lcv = L(fine_level - 1);
+    materialize_u(lcv);
+    materialize_u(lf);
     // the last owned fine row (odd) interpolates from the first coarse halo row
     ensure_halo(lcv, W_U, 1);
     launch_prolong<T>(stream, lc, (const T*)lcv.u[lcv.cur], lcv.pitch, (T*)lf.u[lf.cur], lf.pitch, lf.N, lf.own_lo,

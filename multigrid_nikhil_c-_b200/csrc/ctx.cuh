@@ -59,6 +59,9 @@ struct Level {
     // number of valid halo rows (distributed levels) of the current u, of f and of r;
     // an operator that rewrites only the owned rows sets it to 0, Ctx::ensure_halo exchanges lazily
     int hv_u = 0, hv_f = 0, hv_r = 0;
+    // MGB200_ZERO_GUESS: the current u is LOGICALLY zero but its buffer was not written (the next kernel is a
+    // zero-guess variant that does not read it); Ctx::materialize_u writes the zeros for every other reader
+    bool u_zero = false;
 };
 
 struct GraphEntry {
@@ -87,6 +90,7 @@ struct Ctx {
     Comm* comm = nullptr;
     int aggl_level = 0;  // levels <= aggl_level are replicated on every rank
     bool graph_dist = false;  // capture NCCL exchanges into cycle graphs (MGB200_GRAPH_DIST=1)
+    bool zero_guess = false;  // skip reading / writing the zero coarse guess (MGB200_ZERO_GUESS=1)
     bool comm_avoid = false;  // communication-avoiding slab schedule (MGB200_COMM_AVOID=1, csrc/sched.h)
 
     explicit Ctx(const mg_config& c);
@@ -118,6 +122,7 @@ struct Ctx {
 
     void sync();
     void ensure_halo(Level& lv, Which w, int depth);
+    void materialize_u(Level& lv);
     void set_halo(Level& lv, Which w, int depth);
     // host-side state a captured cycle depends on and changes: which u buffer is current on each level and,
     // on distributed levels, how many halo rows of u / f / r are valid (decides which exchanges were captured)

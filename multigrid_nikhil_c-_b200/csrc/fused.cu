@@ -4,6 +4,7 @@
 #include "fused.cuh"
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 #include <cstdlib>
 
@@ -85,7 +86,7 @@ static int default_ry(const Level& lv, int strips)
 }
 
 template <typename T, int NS, int MODE>
-static StreamArgs<T> make_args(Ctx& ctx, Level& lv, Level* lcv, int ry, int ya = -1, int yb = -1)
+static StreamArgs<T> make_args(Ctx& ctx, Level& lv, Level* lcv, int ry, int ya = -1, int yb = -1, bool write_zero_guess = true)
 {
     typedef StreamCfg<T, NS, MODE> C;
     StreamArgs<T> a;
@@ -116,7 +117,7 @@ static StreamArgs<T> make_args(Ctx& ctx, Level& lv, Level* lcv, int ry, int ya =
     a.crow_lo = a.crow_hi = 0;
     if (MODE == MODE_PRE) {
         a.fc = (T*)lcv->f;
-        a.uc = (lv.distributed && !lcv->distributed) ? nullptr : (T*)lcv->u[0];
+        a.uc = ((lv.distributed && !lcv->distributed) || !write_zero_guess) ? nullptr : (T*)lcv->u[0];
         a.pitch_c = lcv->pitch;
         a.Nc = lcv->N;
     } else if (MODE == MODE_POST) {
@@ -197,6 +198,8 @@ template <typename T, int NS, int MODE, bool RBGS>
 static void launch_stream(Ctx& ctx, Level& lv, Level* lcv)
 {
     typedef StreamCfg<T, NS, MODE> C;
+    ctx.materialize_u(lv);
+    if (MODE == MODE_POST) ctx.materialize_u(*lcv);
     // lazy halo exchanges (no-ops on replicated levels): rows the stencil pipeline reaches into
     ctx.ensure_halo(lv, Ctx::W_U, C::HT - (MODE == MODE_POST ? 1 : 0));
     ctx.ensure_halo(lv, Ctx::W_F, NS + (MODE == MODE_PRE ? 1 : 0) - (MODE == MODE_SWEEPS ? 1 : 0));
@@ -208,6 +211,7 @@ static void launch_stream(Ctx& ctx, Level& lv, Level* lcv)
     lv.cur ^= 1;
     lv.hv_u = 0;
     if (MODE == MODE_PRE) {
+        lcv->u_zero = false;   // the zero guess is written (kernel stores or the memset below)
         if (lv.distributed && !lcv->distributed) {
             // agglomeration: gather the coarse right-hand side everywhere, zero guess on the full grid
             comm_allgather_rows(ctx, *lcv, lcv->f);
@@ -270,6 +274,8 @@ static void launch_tile_cfg(Ctx& ctx, Level& lv, Level* lcv)
 template <typename T, int NS, int MODE, bool RBGS>
 static void launch_tile(Ctx& ctx, Level& lv, Level* lcv)
 {
+    ctx.materialize_u(lv);
+    if (MODE == TILE_POST) ctx.materialize_u(*lcv);
     // same halo contract as the streaming kernels (MODE values coincide)
     ctx.ensure_halo(lv, Ctx::W_U, NS + (MODE == TILE_PRE ? 2 : 0));
     ctx.ensure_halo(lv, Ctx::W_F, NS + (MODE == TILE_PRE ? 1 : 0) - (MODE == TILE_SWEEPS ? 1 : 0));
@@ -280,6 +286,7 @@ static void launch_tile(Ctx& ctx, Level& lv, Level* lcv)
     lv.cur ^= 1;
     lv.hv_u = 0;
     if (MODE == TILE_PRE) {
+        lcv->u_zero = false;
         if (lv.distributed && !lcv->distributed) {
             comm_allgather_rows(ctx, *lcv, lcv->f);
             MG_CK(cudaMemsetAsync(lcv->alloc[0], 0, lcv->bytes, ctx.stream));
@@ -311,6 +318,50 @@ int fused_jacobi(Ctx& ctx, Level& lv, int remaining, T, T)
 template int fused_jacobi<double>(Ctx&, Level&, int, double, double);
 template int fused_jacobi<float>(Ctx&, Level&, int, float, float);
 
+// ---------------------------------------------------------------------------------
+// zero-guess chain (opt-in MGB200_ZERO_GUESS=1): PRE(l) does not write the zero coarse guess when the first
+// kernel of level l-1 is a zero-guess variant that does not read u either (the stream PRE or the tail).
+// Saves S/4 bytes per fine point in PRE(l) and S per point in PRE(l-1).  Any other reader of a logically-zero
+// iterate goes through Ctx::materialize_u, so a wrong prediction costs time, never correctness.
+// ---------------------------------------------------------------------------------
+static int tail_top(const Ctx& ctx);
+static bool use_tile(const Level& lv);
+
+static bool child_takes_zero_guess(Ctx& ctx, Level& lv, int nu1)
+{
+    if (!ctx.zero_guess || !(ctx.cfg.flags & MG_FUSED) || lv.distributed) return false;
+    const int c = lv.level - 1;
+    if (c < ctx.cfg.coarsest_level || ctx.L(c).distributed) return false;
+    if (c == tail_top(ctx)) return true;
+    if (c <= ctx.cfg.coarsest_level) return false;
+    return nu1 >= 1 && nu1 <= 2 && !use_tile(ctx.L(c));
+}
+
+template <typename T, int NS, bool RBGS>
+static void launch_pre_zero_guess(Ctx& ctx, Level& lv, Level* lcv, bool write_zero_guess)
+{
+    // u == 0 needs no halo; f as for PRE
+    ctx.ensure_halo(lv, Ctx::W_F, NS + 1);
+    lcv->cur = 0;
+    const int ry = tuned_ry<T, NS, MODE_PRE, RBGS>(ctx, lv, lcv);
+    const StreamArgs<T> a = make_args<T, NS, MODE_PRE>(ctx, lv, lcv, ry, -1, -1, write_zero_guess);
+    if (a.yb > a.ya) {
+        typedef StreamCfg<T, NS, MODE_PRE> C;
+        static bool attr_set = false;
+        if (!attr_set) {
+            MG_CK(cudaFuncSetAttribute(k_stream_pre_zg<T, NS, RBGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_set = true;
+        }
+        const size_t smem = std::min<size_t>(100 * 1024, std::max<size_t>(C::SMEM_BYTES, (size_t)(227 * 1024) / std::max(1, g_occ / kStreamWarps) - 1024));
+        k_stream_pre_zg<T, NS, RBGS><<<cdiv(a.nitems, kStreamWarps), kStreamWarps * 32, smem, ctx.stream>>>(a);
+        ++ctx.lc.n;
+        MG_CK(cudaGetLastError());
+    }
+    lv.cur ^= 1;
+    lv.hv_u = 0;
+    lv.u_zero = false;
+}
+
 template <typename T>
 static void stream_sweeps(Ctx& ctx, Level& lv, int nu)
 {
@@ -328,6 +379,49 @@ template <typename T>
 static void pre_fused(Ctx& ctx, Level& lv, Level& lcv, int nu1)
 {
     const int k = std::min(nu1, 2);
+    const bool rb = ctx.cfg.smoother == MG_SMOOTH_RBGS;
+    if (ctx.zero_guess && !use_tile(lv) && !lv.distributed) {
+        // opt-in zero-guess chain
+        const bool wz = !child_takes_zero_guess(ctx, lv, nu1);
+        if (lv.u_zero && nu1 == k) {
+            if (!rb) {
+                if (k == 2) launch_pre_zero_guess<T, 2, false>(ctx, lv, &lcv, wz);
+                else launch_pre_zero_guess<T, 1, false>(ctx, lv, &lcv, wz);
+            } else {
+                if (k == 2) launch_pre_zero_guess<T, 4, true>(ctx, lv, &lcv, wz);
+                else launch_pre_zero_guess<T, 2, true>(ctx, lv, &lcv, wz);
+            }
+            lcv.u_zero = !wz;   // zeros were written unless the child skips reading them
+            lcv.cur = 0;
+            return;
+        }
+        if (!wz) {
+            // regular PRE that skips the zero-guess store
+            ctx.materialize_u(lv);
+            stream_sweeps<T>(ctx, lv, nu1 - k);
+            ctx.ensure_halo(lv, Ctx::W_U, (rb ? 2 * k : k) + 2);
+            ctx.ensure_halo(lv, Ctx::W_F, (rb ? 2 * k : k) + 1);
+            lcv.cur = 0;
+            auto go = [&](auto ns_tag, auto rb_tag) {
+                constexpr int NS = decltype(ns_tag)::value;
+                constexpr bool RB = decltype(rb_tag)::value;
+                const int ry = tuned_ry<T, NS, MODE_PRE, RB>(ctx, lv, &lcv);
+                const StreamArgs<T> a = make_args<T, NS, MODE_PRE>(ctx, lv, &lcv, ry, -1, -1, false);
+                raw_launch<T, NS, MODE_PRE, RB>(ctx, a);
+            };
+            if (!rb) {
+                if (k == 2) go(std::integral_constant<int, 2>(), std::false_type());
+                else go(std::integral_constant<int, 1>(), std::false_type());
+            } else {
+                if (k == 2) go(std::integral_constant<int, 4>(), std::true_type());
+                else go(std::integral_constant<int, 2>(), std::true_type());
+            }
+            lv.cur ^= 1;
+            lv.hv_u = 0;
+            lcv.u_zero = true;
+            return;
+        }
+    }
     stream_sweeps<T>(ctx, lv, nu1 - k);
     if (use_tile(lv)) {
         if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) {
@@ -403,7 +497,18 @@ static void run_tail(Ctx& ctx, int level, int nu1, int nu2, int gamma)
     a.f = (const T*)lv.f;
     a.pitch = lv.pitch;
     const size_t smem = tail_smem_bytes<T>(level, a.coarsest);
-    if (ctx.cfg.smoother == MG_SMOOTH_RBGS) k_tail<T, true><<<1, kTailThreads, smem, ctx.stream>>>(a);
+    if (lv.u_zero) {   // opt-in zero-guess chain: u is logically zero and is not read
+        static bool attr_set = false;
+        if (!attr_set) {
+            MG_CK(cudaFuncSetAttribute(k_tail_zg<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem_bytes<T>(kTailMaxLevel, 1)));
+            MG_CK(cudaFuncSetAttribute(k_tail_zg<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem_bytes<T>(kTailMaxLevel, 1)));
+            attr_set = true;
+        }
+        if (ctx.cfg.smoother == MG_SMOOTH_RBGS) k_tail_zg<T, true><<<1, kTailThreads, smem, ctx.stream>>>(a);
+        else k_tail_zg<T, false><<<1, kTailThreads, smem, ctx.stream>>>(a);
+        lv.u_zero = false;
+        lv.hv_u = lv.halo;
+    } else if (ctx.cfg.smoother == MG_SMOOTH_RBGS) k_tail<T, true><<<1, kTailThreads, smem, ctx.stream>>>(a);
     else k_tail<T, false><<<1, kTailThreads, smem, ctx.stream>>>(a);
     ++ctx.lc.n;
     MG_CK(cudaGetLastError());
@@ -427,6 +532,7 @@ template <typename T>
 static void comm_avoid_run(Ctx& ctx, const SchedPlan& plan, int nu1, int nu2)
 {
     const bool rb = ctx.cfg.smoother == MG_SMOOTH_RBGS;
+    ctx.materialize_u(ctx.L(plan.ops.front().level));
     for (const SchedOp& op : plan.ops) {
         Level& lv = ctx.L(op.level);
         switch (op.kind) {
@@ -446,6 +552,7 @@ static void comm_avoid_run(Ctx& ctx, const SchedPlan& plan, int nu1, int nu2)
                     else launch_stream_range<T, 2, MODE_PRE, true>(ctx, lv, &lcv, op.a, op.b);
                 }
                 lv.hv_u = plan.e[op.level];
+                lcv.u_zero = false;
                 if (lcv.distributed) {
                     lcv.hv_f = plan.e[op.level] / 2;
                     lcv.hv_u = lcv.halo;

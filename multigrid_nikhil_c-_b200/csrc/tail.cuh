@@ -151,7 +151,7 @@ __device__ __noinline__ void tail_visit(T* base, const TailArgs<T>& a, unsigned&
     }
 }
 
-template <typename T, bool RBGS, int TOP>
+template <typename T, bool RBGS, int TOP, bool ZG = false>
 __device__ __forceinline__ void tail_run(T* base, const TailArgs<T>& a, int warp, int lane)
 {
     typedef TailLv<T, TOP> LV;
@@ -166,7 +166,7 @@ __device__ __forceinline__ void tail_run(T* base, const TailArgs<T>& a, int warp
             for (int h = 0; h < LV::XIT; ++h) {
                 const int y = 1 + warp + it * kTailWarps, x = 1 + lane + 32 * h;
                 const bool ok = (y < LV::N) && (x < LV::N);
-                tu[it][h] = ok ? a.u[(i64)y * a.pitch + x] : (T)0;
+                tu[it][h] = (ok && !ZG) ? a.u[(i64)y * a.pitch + x] : (T)0;
                 tf[it][h] = ok ? a.f[(i64)y * a.pitch + x] : (T)0;
             }
         T* A = lv.A(cur);
@@ -207,6 +207,28 @@ k_tail(const TailArgs<T> a)
         case 4: tail_run<T, RBGS, 4>(base, a, warp, lane); break;
         case 5: tail_run<T, RBGS, 5>(base, a, warp, lane); break;
         default: tail_run<T, RBGS, 6>(base, a, warp, lane); break;
+    }
+}
+
+// zero-guess variant (opt-in, MGB200_ZERO_GUESS=1): u of the top level is known to be zero and is not read.
+// A separate kernel so that k_tail stays byte-identical to the GPU-verified build.
+template <typename T, bool RBGS>
+__global__ void __launch_bounds__(kTailThreads)
+k_tail_zg(const TailArgs<T> a)
+{
+    extern __shared__ __align__(16) unsigned char tail_smem[];
+    T* base = reinterpret_cast<T*>(tail_smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = tail_off(a.top + 1);
+    for (int i = threadIdx.x; i < total; i += kTailThreads) base[i] = (T)0;
+    __syncthreads();
+    switch (a.top) {
+        case 1: tail_run<T, RBGS, 1, true>(base, a, warp, lane); break;
+        case 2: tail_run<T, RBGS, 2, true>(base, a, warp, lane); break;
+        case 3: tail_run<T, RBGS, 3, true>(base, a, warp, lane); break;
+        case 4: tail_run<T, RBGS, 4, true>(base, a, warp, lane); break;
+        case 5: tail_run<T, RBGS, 5, true>(base, a, warp, lane); break;
+        default: tail_run<T, RBGS, 6, true>(base, a, warp, lane); break;
     }
 }
 

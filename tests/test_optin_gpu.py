@@ -55,6 +55,33 @@ def test_tile_kernels_cycles_bitwise(mgb, orc, knob, level, dtype, smoother, nu1
                 assert_bitwise(mg.get_u(level), want[k + 1], f"tile cycle {k + 1} graph={graph} tail={tail}")
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("smoother,nu1,nu2,gamma", [("jacobi", 2, 2, 1), ("jacobi", 1, 2, 2), ("rbgs", 2, 2, 1), ("rbgs", 1, 1, 2),
+                                                    ("jacobi", 3, 2, 1)])
+@pytest.mark.parametrize("level", [4, 7, 8, 10])
+def test_zero_guess_chain_bitwise(mgb, orc, knob, level, dtype, smoother, nu1, nu2, gamma):
+    """MGB200_ZERO_GUESS=1: PRE skips the zero coarse guess store, the next level's PRE / the tail do not read u."""
+    knob("MGB200_ZERO_GUESS", "1")
+    x, b = rand_vec(level, dtype, 83), rand_vec(level, dtype, 84, 1e-3)
+    p = oracle.Params(nu1=nu1, nu2=nu2, gamma=gamma, smoother=1 if smoother == "rbgs" else 0, nthreads=4)
+    want = [x]
+    for _ in range(3):
+        want.append(orc.vcyclemultigrid(want[-1], b, p))
+    for graph, tail in ((False, False), (False, True), (True, True)):
+        with mgb.Multigrid(level, dtype=dtype, smoother=smoother, graph=graph, fused=True, coarse_tail=tail) as mg:
+            mg.set_u(level, x)
+            mg.set_rhs(level, b)
+            for k in range(3):
+                mg.cycle(level, nu1, nu2, gamma)
+                assert_bitwise(mg.get_u(level), want[k + 1], f"zero-guess cycle {k + 1} graph={graph} tail={tail}")
+            # every API that reads a coarse iterate must see real zeros
+            if level > 2:
+                mg.residual(level)
+                mg.restrict(level)
+                assert not mg.get_u(level - 1).any()
+            assert_bitwise(mg.fullmultigrid(b, 1, nu1, nu2), orc.fullmultigrid(b, 1, p), "fmg with zero-guess chain")
+
+
 def test_tile_kernels_full_size_and_speed(mgb, orc, knob):
     """4097^2: the tile kernels take over levels <= 10; result must not change, cycle must not get slower."""
     level = 12
