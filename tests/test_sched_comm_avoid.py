@@ -179,3 +179,73 @@ def test_plan_extents_and_tightness(mgb):
     assert plan[0][3] == 94 and plan[1][3] == 93                 # u: e+NS1+2, f: e+NS1+1
     assert lib.mg_plan_vcycle(14, 10, 1, 0, 2, 2, 0, 0, ops, 100, halo) == -1      # single GPU: not applicable
     assert lib.mg_plan_vcycle(8, 4, 8, 0, 2, 2, 0, 0, ops, 100, halo) == -1        # slabs thinner than the halo
+
+
+# ------------------------------------------------------------------------------------------------
+# In-process simulation of ALL ranks (no process group): cheap enough for the real hierarchy shape of the
+# 16385^2 / 8-GPU configuration (four distributed levels above the agglomeration level), scaled down.
+# ------------------------------------------------------------------------------------------------
+class SimRanks:
+    def __init__(self, lib, orc, top, aggl, world, ns1, ns2, rbgs=False):
+        self.lib, self.o, self.top, self.aggl, self.world = lib, orc, top, aggl, world
+        self.emus, self.plans = [], []
+        for r in range(world):
+            ops = (ctypes.c_int * 400)()
+            halo = (ctypes.c_int * 32)()
+            nops = lib.mg_plan_vcycle(top, aggl, world, r, ns1, ns2, 0, 10 ** 6, ops, 100, halo)
+            assert nops > 0
+            self.plans.append([tuple(ops[4 * i:4 * i + 4]) for i in range(nops)])
+            self.emus.append(TraceEmu(lib, orc, top, aggl, r, world, ns1, ns2, list(halo), rbgs))
+        assert len({tuple(k for k, *_ in p) for p in self.plans}) == 1, "ranks disagree on the op sequence"
+
+    def run(self):
+        nops = len(self.plans[0])
+        for i in range(nops):
+            kind, l = self.plans[0][i][0], self.plans[0][i][1]
+            if kind == EXCH:
+                which, depth = self.plans[0][i][2], self.plans[0][i][3]
+                arrs = [(e.u[l] if which == 0 else e.f[l]) for e in self.emus]
+                snap = [a.copy() for a in arrs]
+                for r, e in enumerate(self.emus):
+                    a, b = e.own[l]
+                    if r > 0:
+                        pa, pb = self.emus[r - 1].own[l]
+                        arrs[r][a - 1 - depth:a - 1] = snap[r - 1][pb - 1 - depth:pb - 1]
+                    if r < self.world - 1:
+                        na, nb = self.emus[r + 1].own[l]
+                        arrs[r][b - 1:b - 1 + depth] = snap[r + 1][na - 1:na - 1 + depth]
+            elif kind == GATHER_F:
+                parts = []
+                aa, bb = ctypes.c_int(), ctypes.c_int()
+                for r, e in enumerate(self.emus):
+                    self.lib.mg_slab_rows(l, r, self.world, ctypes.byref(aa), ctypes.byref(bb))
+                    parts.append(e.f[l][aa.value - 1:bb.value - 1].copy())
+                full = np.concatenate(parts, axis=0)
+                for e in self.emus:
+                    e.f[l] = full.copy()
+                    e.u[l] = np.zeros_like(full)
+            else:
+                for r, e in enumerate(self.emus):
+                    e.run([self.plans[r][i]])
+
+
+@pytest.mark.parametrize("world,top,aggl,ns1,ns2,rbgs", [(8, 10, 6, 2, 2, False), (4, 9, 5, 2, 2, False), (8, 10, 7, 1, 2, False),
+                                                        (4, 10, 6, 4, 4, True), (2, 7, 4, 2, 2, False)])
+def test_comm_avoiding_schedule_all_ranks_in_process(mgb, orc, world, top, aggl, ns1, ns2, rbgs):
+    import oracle
+    from conftest import rand_vec
+    lib = mgb.capi.lib()
+    sim = SimRanks(lib, orc, top, aggl, world, ns1, ns2, rbgs)
+    x, b = rand_vec(top, np.float64, 73), rand_vec(top, np.float64, 74, 1e-3)
+    for e in sim.emus:
+        e.u[top] = e.keep(top, x, e.own[top])
+        e.f[top] = e.keep(top, b, e.stored(top))
+    sim.run()
+    pp = oracle.Params(nu1=ns1 // 2, nu2=ns2 // 2, smoother=1, nthreads=4) if rbgs else oracle.Params(nu1=ns1, nu2=ns2, nthreads=4)
+    n = (1 << top) - 1
+    want = orc.vcyclemultigrid(x, b, pp).reshape(n, n)
+    for r, e in enumerate(sim.emus):
+        a, bb = e.own[top]
+        got = e.u[top][a - 1:bb - 1]
+        assert not np.isnan(got).any(), f"rank {r}: owned rows depend on rows the schedule did not provide"
+        assert np.array_equal(got, want[a - 1:bb - 1]), f"rank {r}"
