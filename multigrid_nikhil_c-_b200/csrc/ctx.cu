@@ -151,6 +151,8 @@ Ctx::~Ctx()
     if (stream) cudaStreamSynchronize(stream);
     for (auto& kv : graphs)
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    for (auto& kv : ctail_ops)
+        if (kv.second.first) cudaFree(kv.second.first);
     if (comm) comm_destroy(comm);
     for (auto& lv : levels)
         for (int k = 0; k < 4; ++k)
@@ -445,7 +447,7 @@ void Ctx::cycle(int level, int nu1, int nu2, int gamma)
     auto key = std::make_tuple(level, nu1, nu2, gamma, state_blob());
     auto it = graphs.find(key);
     if (it == graphs.end()) {
-        fused_pretune(*this, level, nu1, nu2);
+        fused_pretune(*this, level, nu1, nu2, gamma);
         GraphEntry ge;
         const long long before = lc.n;
         cudaGraph_t g = nullptr;

@@ -87,6 +87,7 @@ struct Ctx {
     bool capturing = false;
     std::map<std::tuple<int, int, int, int, std::string>, GraphEntry> graphs;
     std::map<std::tuple<int, int, int, int>, int> stream_ry;  // tuned chunk height per (level, mode, NS, rbgs)
+    std::map<std::tuple<int, int, int, int>, std::pair<void*, int>> ctail_ops;  // cluster-tail op lists on the device
     Comm* comm = nullptr;
     int aggl_level = 0;  // levels <= aggl_level are replicated on every rank
     bool graph_dist = false;  // capture NCCL exchanges into cycle graphs (MGB200_GRAPH_DIST=1)

@@ -13,12 +13,15 @@
 #include "stream.cuh"
 #include "tail.cuh"
 #include "tile.cuh"
+#include "ctail.cuh"
 
 namespace mgb {
 
 static int g_num_sms = 148;
 static int g_force_ry = 0;
 static int g_force_ry_minN = 4096;
+static bool g_ctail = false;     // MGB200_CTAIL=1: cluster coarse tail for levels <= 8 (experimental, see ctail.cuh)
+static int g_ctail_ctas = 16;    // MGB200_CTAIL_CTAS: cluster size (power of two <= 16; > 8 is a non-portable cluster size)
 static bool g_tile = false;      // MGB200_TILE=1: shared-memory tile kernels on the mid levels (experimental, see tile.cuh)
 static int g_tile_maxN = 1024;
 static bool g_autotune = true;   // MGB200_AUTOTUNE=0 disables the chunk-height tuner
@@ -63,6 +66,8 @@ void fused_setup(Ctx& ctx)
     if (const char* e = getenv("MGB200_STREAM_OCC")) g_occ = std::max(1, atoi(e));
     if (const char* e = getenv("MGB200_AUTOTUNE")) g_autotune = atoi(e) != 0;
     if (const char* e = getenv("MGB200_TILE")) g_tile = atoi(e) != 0;
+    if (const char* e = getenv("MGB200_CTAIL")) g_ctail = atoi(e) != 0;
+    if (const char* e = getenv("MGB200_CTAIL_CTAS")) g_ctail_ctas = std::max(1, std::min(kCtailMaxCtas, atoi(e)));
     if (const char* e = getenv("MGB200_TILE_MAXN")) g_tile_maxN = atoi(e);
     if (ctx.f64()) set_attrs_t<double>();
     else set_attrs_t<float>();
@@ -515,6 +520,78 @@ static void run_tail(Ctx& ctx, int level, int nu1, int nu2, int gamma)
 }
 
 // ---------------------------------------------------------------------------------
+// cluster coarse tail (ctail_core.h), opt-in MGB200_CTAIL=1: levels <= ctail_top in one cluster launch
+// ---------------------------------------------------------------------------------
+static int ctail_top(const Ctx& ctx)
+{
+    if (!g_ctail || (g_ctail_ctas & (g_ctail_ctas - 1))) return -1;
+    int top = std::min(kCtailMaxLevel, ctx.cfg.finest_level);
+    while (top >= ctx.cfg.coarsest_level) {
+        const size_t bytes = ctx.f64() ? ctail_smem_bytes<double>(top, g_ctail_ctas) : ctail_smem_bytes<float>(top, g_ctail_ctas);
+        if (bytes <= 227 * 1024) break;
+        --top;
+    }
+    if (top < ctx.cfg.coarsest_level || ctx.L(top).distributed) return -1;
+    return top;
+}
+
+// the op list of a cycle visit, uploaded once per (level, nu1, nu2, gamma); must exist before graph capture
+static const CtailOp* ctail_ops(Ctx& ctx, int level, int nu1, int nu2, int gamma, int* nops)
+{
+    const auto key = std::make_tuple(level, nu1, nu2, gamma);
+    auto it = ctx.ctail_ops.find(key);
+    if (it == ctx.ctail_ops.end()) {
+        if (ctx.capturing) throw MgError(MG_ERR_STATE, "cluster-tail schedule requested during graph capture");
+        const std::vector<CtailOp> ops = ctail_schedule(level, ctx.cfg.coarsest_level, nu1, nu2, gamma, ctx.cfg.smoother == MG_SMOOTH_RBGS);
+        void* d = nullptr;
+        MG_CK(cudaMalloc(&d, ops.size() * sizeof(CtailOp)));
+        MG_CK(cudaMemcpy(d, ops.data(), ops.size() * sizeof(CtailOp), cudaMemcpyHostToDevice));
+        it = ctx.ctail_ops.emplace(key, std::make_pair(d, (int)ops.size())).first;
+    }
+    *nops = it->second.second;
+    return (const CtailOp*)it->second.first;
+}
+
+template <typename T>
+static void run_ctail(Ctx& ctx, int level, int nu1, int nu2, int gamma)
+{
+    Level& lv = ctx.L(level);
+    ctx.materialize_u(lv);
+    CtailArgs<T> a;
+    a.top = level;
+    a.nctas = g_ctail_ctas;
+    a.ops = ctail_ops(ctx, level, nu1, nu2, gamma, &a.nops);
+    const T om = (T)ctx.cfg.omega;
+    a.c0 = (T)(1.0 - (double)om);
+    a.c1 = (T)((double)om / 4.0);
+    a.w = (T)ctx.cfg.restrict_weight;
+    a.u = (T*)lv.u[lv.cur];
+    a.f = (const T*)lv.f;
+    a.pitch = lv.pitch;
+    const size_t smem = ctail_smem_bytes<T>(level, g_ctail_ctas);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MG_CK(cudaFuncSetAttribute(k_ctail<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MG_CK(cudaFuncSetAttribute(k_ctail<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)g_ctail_ctas);
+    cfg.blockDim = dim3(kCtailThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)g_ctail_ctas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MG_CK(cudaLaunchKernelEx(&cfg, k_ctail<T>, a));
+    ++ctx.lc.n;
+}
+
+// ---------------------------------------------------------------------------------
 // communication-avoiding V-cycle over the distributed levels (sched.h), opt-in MGB200_COMM_AVOID=1.
 // The op list comes from the same planner the CPU emulation test executes with the oracle.
 // ---------------------------------------------------------------------------------
@@ -602,6 +679,11 @@ static bool comm_avoid_cycle(Ctx& ctx, int level, int nu1, int nu2, int gamma)
 bool fused_cycle_level(Ctx& ctx, int level, int nu1, int nu2, int gamma)
 {
     if (comm_avoid_cycle(ctx, level, nu1, nu2, gamma)) return true;
+    if (level == ctail_top(ctx)) {
+        if (ctx.f64()) run_ctail<double>(ctx, level, nu1, nu2, gamma);
+        else run_ctail<float>(ctx, level, nu1, nu2, gamma);
+        return true;
+    }
     if (level == tail_top(ctx)) {
         if (ctx.f64()) run_tail<double>(ctx, level, nu1, nu2, gamma);
         else run_tail<float>(ctx, level, nu1, nu2, gamma);
@@ -644,8 +726,12 @@ static void pretune_t(Ctx& ctx, int level, int nu1, int nu2)
     }
 }
 
-void fused_pretune(Ctx& ctx, int level, int nu1, int nu2)
+void fused_pretune(Ctx& ctx, int level, int nu1, int nu2, int gamma)
 {
+    {   // the cluster tail's op list must be on the device before a graph is captured
+        const int ct = ctail_top(ctx);
+        if (ct >= 0 && ct <= level) { int n; ctail_ops(ctx, ct, nu1, nu2, gamma, &n); }
+    }
     if (!(ctx.cfg.flags & MG_FUSED) || nu1 < 1 || nu2 < 1) return;
     if (ctx.f64()) pretune_t<double>(ctx, level, nu1, nu2);
     else pretune_t<float>(ctx, level, nu1, nu2);

@@ -12,7 +12,7 @@ template <typename T> int fused_jacobi(Ctx& ctx, Level& lv, int remaining, T c0,
 // run one whole cycle visit of `level` with fused kernels; false = caller runs the unfused sequence
 bool fused_cycle_level(Ctx& ctx, int level, int nu1, int nu2, int gamma);
 // choose chunk heights for the big levels before a cycle graph is captured
-void fused_pretune(Ctx& ctx, int level, int nu1, int nu2);
+void fused_pretune(Ctx& ctx, int level, int nu1, int nu2, int gamma);
 // one launch of the fused pre- (true) or post-smoothing (false) kernel for timing; false if unavailable
 bool fused_time_hook(Ctx& ctx, int level, bool pre);
 // micro-benchmark only: four weighted-Jacobi sweeps temporally blocked in one launch (not used by the cycles)

@@ -82,6 +82,28 @@ def test_zero_guess_chain_bitwise(mgb, orc, knob, level, dtype, smoother, nu1, n
             assert_bitwise(mg.fullmultigrid(b, 1, nu1, nu2), orc.fullmultigrid(b, 1, p), "fmg with zero-guess chain")
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("ctas", ["16", "8", "4", "1"])
+@pytest.mark.parametrize("level", [3, 6, 8, 10])
+def test_cluster_tail_cycles_bitwise(mgb, orc, knob, level, ctas, dtype):
+    """MGB200_CTAIL=1: levels <= 8 (fewer for small clusters) in one thread-block-cluster launch (DSMEM)."""
+    knob("MGB200_CTAIL", "1")
+    knob("MGB200_CTAIL_CTAS", ctas)
+    x, b = rand_vec(level, dtype, 85), rand_vec(level, dtype, 86, 1e-3)
+    for smoother, nu1, nu2, gamma in (("jacobi", 2, 2, 1), ("jacobi", 1, 2, 2), ("rbgs", 2, 2, 1), ("rbgs", 1, 1, 2)):
+        p = oracle.Params(nu1=nu1, nu2=nu2, gamma=gamma, smoother=1 if smoother == "rbgs" else 0, nthreads=4)
+        want = [x]
+        for _ in range(2):
+            want.append(orc.vcyclemultigrid(want[-1], b, p))
+        for graph in (False, True):
+            with mgb.Multigrid(level, dtype=dtype, smoother=smoother, graph=graph) as mg:
+                mg.set_u(level, x)
+                mg.set_rhs(level, b)
+                for k in range(2):
+                    mg.cycle(level, nu1, nu2, gamma)
+                    assert_bitwise(mg.get_u(level), want[k + 1], f"ctail cycle {k + 1} C={ctas} graph={graph} {smoother} g={gamma}")
+
+
 def test_tile_kernels_full_size_and_speed(mgb, orc, knob):
     """4097^2: the tile kernels take over levels <= 10; result must not change, cycle must not get slower."""
     level = 12
