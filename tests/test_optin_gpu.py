@@ -134,3 +134,55 @@ def test_multigpu_optin_paths(env):
            "--master-port", "29577", os.path.join(ROOT, "tests", "mgpu_worker.py")]
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900, env={**os.environ, **env})
     assert out.returncode == 0 and "MGPU OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs 3-5 at FULL size on one GPU (minutes of oracle time and tens of GB of host memory:
+# opt-in).  Bit-exact where the oracle finishes in reasonable time, size-independent properties otherwise.
+# ------------------------------------------------------------------------------------------------
+def test_config3_16385_rbgs_vcycle_bitwise(mgb, orc):
+    level = 14
+    n = (1 << level) - 1
+    b = (1.0 / (1 << level)) ** 2 * np.random.default_rng(1234).uniform(-1, 1, n * n)
+    p = oracle.Params(smoother=1, nthreads=orc.max_threads())
+    with mgb.Multigrid(level, smoother="rbgs") as mg:
+        mg.set_rhs(level, b)
+        mg.zero_u(level)
+        r0 = mg.residual(level, norm=True)
+        mg.cycle(level, 2, 2, 1)
+        r1 = mg.residual(level, norm=True)
+        assert_bitwise(mg.get_u(level), orc.vcyclemultigrid(np.zeros(n * n), b, p), "RB-GS V(2,2) at 16385^2")
+        assert r1 / r0 < 0.1
+
+
+def test_config4_8193_wcycle_and_fmg_bitwise(mgb, orc):
+    level = 13
+    n = (1 << level) - 1
+    b = (1.0 / (1 << level)) ** 2 * np.random.default_rng(1234).uniform(-1, 1, n * n)
+    nt = orc.max_threads()
+    with mgb.Multigrid(level) as mg:
+        mg.set_rhs(level, b)
+        mg.zero_u(level)
+        mg.cycle(level, 2, 2, 2)
+        assert_bitwise(mg.get_u(level), orc.vcyclemultigrid(np.zeros(n * n), b, oracle.Params(gamma=2, nthreads=nt)), "W(2,2) at 8193^2")
+        assert_bitwise(mg.fullmultigrid(b, 1, 2, 2), orc.fullmultigrid(b, 1, oracle.Params(nthreads=nt)), "FMG at 8193^2")
+
+
+def test_config5_32769_fp32_smoother_residual_properties(mgb):
+    """32769^2 fp32 (4.3 GB per array): linearity of smoother and residual under exact scalings, and temporal
+    blocking (two sweeps in one launch) equals two single sweeps."""
+    level = 15
+    with mgb.Multigrid(level, coarsest_level=level - 1, dtype=np.float32) as mg:
+        mg.force_constant(4.0)                      # b = 4 h^2 (exact in fp32)
+        mg.zero_u(level)
+        mg.smooth(level, 2)
+        r1 = mg.residual(level, norm=True)
+        mg.force_constant(8.0)                      # scaling by 2 is exact: every iterate and the norm double
+        mg.zero_u(level)
+        mg.smooth(level, 2)
+        r2 = mg.residual(level, norm=True)
+        assert r2 == 2.0 * r1
+        mg.zero_u(level)
+        mg.smooth(level, 1)
+        mg.smooth(level, 1)
+        assert mg.residual(level, norm=True) == r2
