@@ -16,6 +16,14 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def free_port():
+    """a TCP port nobody listens on right now (rendezvous of the gloo process group)"""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
 EXCH, PRE, POST, GATHER_F, REPL_CYCLE = range(5)
 
 
@@ -156,7 +164,7 @@ def _worker(rank, world, port, top, aggl, ns1, ns2, q, rbgs=False):
 def test_comm_avoiding_schedule_is_sufficient(world, top, aggl, ns1, ns2, rbgs):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + world * 10 + top + aggl + ns1 * 3 + ns2 + (50 if rbgs else 0)
+    port = free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, top, aggl, ns1, ns2, q, rbgs)) for r in range(world)]
     for pr in procs:
         pr.start()

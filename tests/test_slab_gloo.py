@@ -14,6 +14,14 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def free_port():
+    """a TCP port nobody listens on right now (rendezvous of the gloo process group)"""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def _worker(rank, world, port, level, aggl, smoother, gamma, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -54,7 +62,7 @@ def _worker(rank, world, port, level, aggl, smoother, gamma, q):
 def test_slab_schedule_matches_single_domain(world, level, aggl, smoother, gamma):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + world * 10 + level + aggl + smoother + gamma
+    port = free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, level, aggl, smoother, gamma, q)) for r in range(world)]
     for pr in procs:
         pr.start()
