@@ -19,7 +19,10 @@ def _ngpu():
 def test_slabs_match_oracle(world):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    port = 29500 + world
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:   # a free rendezvous port
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py")]
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
