@@ -93,24 +93,26 @@ struct CtailEnv {
 template <typename T, typename Remote>
 struct CtailLevel {
     const CtailEnv<T, Remote>& env;
-    int N, P, ca, rows_per, off, be;
+    int N, P, ca, rows_per, rp_shift, off, be;
     MG_HD CtailLevel(const CtailEnv<T, Remote>& e, int level) : env(e)
     {
         N = 1 << level;
         P = N + 1;
         ca = ctail_active(level, e.nctas);
         rows_per = N / ca;                       // power of two
+        rp_shift = 0;
+        while ((1 << rp_shift) < rows_per) ++rp_shift;
         off = ctail_off(level, e.nctas);
         be = ctail_buf_elems(level, e.nctas);
     }
-    MG_HD int owner(int y) const { const int c = y / rows_per; return c >= ca ? ca - 1 : c; }
+    MG_HD int owner(int y) const { const int c = y >> rp_shift; return c >= ca ? ca - 1 : c; }
     // row y (node row 0..N) of buffer buf (0/1 = u ping / pong-or-residual, 2 = f), wherever it lives
     MG_HD const T* row(int buf, int y) const
     {
         const int c = owner(y);
-        return (c == env.me ? env.smem : env.remote(c)) + off + buf * be + (y - c * rows_per) * P;
+        return (c == env.me ? env.smem : env.remote(c)) + off + buf * be + (y - (c << rp_shift)) * P;
     }
-    MG_HD T* my_row(int buf, int y) const { return env.smem + off + buf * be + (y - env.me * rows_per) * P; }
+    MG_HD T* my_row(int buf, int y) const { return env.smem + off + buf * be + (y - (env.me << rp_shift)) * P; }
     MG_HD int lo() const { return env.me >= ca ? N + 1 : env.me * rows_per; }
     MG_HD int hi() const { return env.me >= ca ? N + 1 : (env.me == ca - 1 ? N + 1 : (env.me + 1) * rows_per); }
 };
