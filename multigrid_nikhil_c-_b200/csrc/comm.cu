@@ -44,6 +44,22 @@ static NcclApi& nccl()
 {
     static NcclApi api;
     if (api.handle) return api;
+#ifdef MGB_EMU
+    // CPU emulation build (tests/host_emul): file-based stand-in, one process per rank
+    api.GetUniqueId = [](ncclUniqueId* id) -> ncclResult_t { return emu_nccl::GetUniqueId(id); };
+    api.CommInitRank = [](ncclComm_t* c, int w, ncclUniqueId id, int r) -> ncclResult_t { return emu_nccl::CommInitRank((emu_nccl::Comm**)c, w, &id, r); };
+    api.CommDestroy = [](ncclComm_t c) -> ncclResult_t { return emu_nccl::CommDestroy((emu_nccl::Comm*)c); };
+    api.Send = [](const void* b, size_t n, int, int peer, ncclComm_t c, cudaStream_t s) -> ncclResult_t { return emu_nccl::Send(b, n, peer, (emu_nccl::Comm*)c, s); };
+    api.Recv = [](void* b, size_t n, int, int peer, ncclComm_t c, cudaStream_t s) -> ncclResult_t { return emu_nccl::Recv(b, n, peer, (emu_nccl::Comm*)c, s); };
+    api.AllGather = [](const void* sb, void* rb, size_t n, int dt, ncclComm_t c, cudaStream_t s) -> ncclResult_t {
+        return emu_nccl::AllGather(sb, rb, n * (dt == ncclFloat64 ? 8 : 1), (emu_nccl::Comm*)c, s);
+    };
+    api.GroupStart = []() -> ncclResult_t { return 0; };
+    api.GroupEnd = []() -> ncclResult_t { return 0; };
+    api.GetErrorString = [](ncclResult_t r) -> const char* { return emu_nccl::GetErrorString(r); };
+    api.handle = &api;
+    return api;
+#endif
     void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (!h) throw MgError(MG_ERR_COMM, std::string("cannot load libnccl.so.2: ") + dlerror());

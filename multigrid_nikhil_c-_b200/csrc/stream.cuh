@@ -86,6 +86,13 @@ struct StreamArgs {
     int crow_lo, crow_hi;  // coarse rows backed by storage
 };
 
+#ifdef MGB_EMU
+// CPU emulation build (tests/host_emul): the copy happens at issue time, which is one of the orders the hardware allows
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) { if (valid) memcpy(smem, gmem, 16); else memset(smem, 0, 16); }
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) { if (valid) memcpy(smem, gmem, 8); else memset(smem, 0, 8); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N> __device__ __forceinline__ void cp_async_wait() {}
+#else
 // cp.async with the `ignore-src` predicate: when !valid nothing is read and zeros are written
 // (maps 1:1 onto LDGSTS.ZFILL with a predicate; `gmem` must still be a mapped address).
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid)
@@ -102,6 +109,7 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool val
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+#endif
 
 // ZG ("zero guess"): the input iterate is known to be identically zero (first visit of a coarse level, P:613):
 // u is neither prefetched nor read, stage 0 is the constant 0.  Same arithmetic on the same values => same bits.

@@ -9,8 +9,25 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+EMULATED = os.environ.get("MGB200_TEST_EMU") == "1"
+
+
+def use_emulated_library():
+    """MGB200_TEST_EMU=1 (set only by tests/test_emulated_library.py for its child pytest runs): point the ctypes
+    binding at tests/host_emul/_build/libmgb200_emu.so -- the product's own csrc/ compiled with g++ against a
+    CUDA-on-CPU emulation -- so that the `gpu`-marked parity tests can also run on a machine without a GPU.
+    Test infrastructure only; the product never loads that library and the real `-m gpu` run never sets the variable."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "host_emul"))
+    import build_emu
+    import mgb200
+    mgb200.capi.LIB_PATH = build_emu.build()
+    mgb200.capi._lib = None
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    if EMULATED:
+        use_emulated_library()
 
 
 @pytest.fixture(scope="session")
