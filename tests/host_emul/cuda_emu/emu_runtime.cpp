@@ -493,6 +493,8 @@ struct Comm {
     long long gather_seq = 0;
 };
 
+static long long g_sends = 0, g_gathers = 0;
+
 static std::string base_dir()
 {
     const char* e = getenv("MGB200_EMU_DIR");
@@ -562,6 +564,7 @@ static int get(const std::string& path, void* buf, size_t bytes)
 int Send(const void* buf, size_t bytes, int peer, Comm* c, cudaStream_t s)
 {
     emu::enqueue(s, [=]() {
+        ++g_sends;
         const long long q = c->send_seq[peer]++;
         if (put(c->dir + "/p2p_" + std::to_string(c->rank) + "_" + std::to_string(peer) + "_" + std::to_string(q), buf, bytes))
             emu::set_error(cudaErrorLaunchFailure);
@@ -582,6 +585,7 @@ int Recv(void* buf, size_t bytes, int peer, Comm* c, cudaStream_t s)
 int AllGather(const void* send, void* recv, size_t bytes, Comm* c, cudaStream_t s)
 {
     emu::enqueue(s, [=]() {
+        ++g_gathers;
         const long long q = c->gather_seq++;
         std::vector<unsigned char> mine((const unsigned char*)send, (const unsigned char*)send + bytes);   // in-place safe
         for (int d = 0; d < c->world; ++d)
@@ -609,5 +613,7 @@ const char* GetErrorString(int r)
 
 }  // namespace emu_nccl
 
+extern "C" long long cuda_emu_nccl_sends() { return emu_nccl::g_sends; }
+extern "C" long long cuda_emu_nccl_allgathers() { return emu_nccl::g_gathers; }
 extern "C" long long cuda_emu_kernels_run() { return emu::g_kernels_run; }
 extern "C" int cuda_emu_live_allocations() { return (int)g_allocs.size(); }

@@ -13,7 +13,15 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import mgb200  # noqa: E402
 import oracle  # noqa: E402
+import conftest  # noqa: E402
 from conftest import rand_vec  # noqa: E402
+
+# MGB200_TEST_EMU=1 (tests/test_emulated_library.py): the same checks on CPU ranks -- gloo instead of nccl for the
+# bootstrap, the CUDA-on-CPU emulation build of the library (tests/host_emul), its file-based NCCL stand-in
+EMU = conftest.EMULATED
+if EMU:
+    conftest.use_emulated_library()
+DEV = "cpu" if EMU else "cuda"
 
 pkg = mgb200.package
 mgdist = __import__("importlib").import_module("multigrid_nikhil_c-_b200.dist")
@@ -29,13 +37,19 @@ def check(mg, level, got, want, what):
 
 def main():
     rank, world, local = mgdist.env_ranks()
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if EMU:
+        dist.init_process_group("gloo")
+        os.environ["LOCAL_RANK"] = "0"   # the emulation has one device
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     o = oracle.get()
     n_checks = 0
     cases = [(np.float64, 7, 4, "jacobi", True), (np.float64, 7, 4, "rbgs", True), (np.float64, 9, 6, "jacobi", True),
              (np.float64, 9, 5, "rbgs", True), (np.float64, 8, 5, "jacobi", False), (np.float64, 8, 6, "rbgs", False),
              (np.float32, 8, 6, "jacobi", True), (np.float32, 8, 5, "rbgs", True), (np.float64, 10, 7, "jacobi", True)]
+    if os.environ.get("MGB200_WORKER_QUICK") == "1":   # bounded run for the CPU suite (tests/test_emulated_library.py)
+        cases = [cases[0], cases[1], cases[7]]
     for dtype, level, aggl, smoother, fused in cases:
             if (1 << (aggl + 1)) // world < 8:
                 continue
@@ -55,7 +69,7 @@ def main():
                 r = o.residual(x, b)
                 check(mg, level, mg.get_r(level), r, "residual")
                 assert abs(nrm - o.norm2(r)) <= 1e-12 * o.norm2(r)
-                t = torch.tensor([nrm], dtype=torch.float64, device="cuda")
+                t = torch.tensor([nrm], dtype=torch.float64, device=DEV)
                 lst = [torch.zeros_like(t) for _ in range(world)]
                 dist.all_gather(lst, t)
                 assert all(float(v.item()) == nrm for v in lst), "norm differs between ranks"
@@ -80,7 +94,13 @@ def main():
                 mg.close()
     dist.barrier()
     if rank == 0:
-        print(f"MGPU OK world={world} checks={n_checks}", flush=True)
+        extra = ""
+        if EMU:   # message counts of the emulated NCCL (lets the caller see that an opt-in schedule really ran)
+            import ctypes
+            L = mgb200.capi.lib()
+            L.cuda_emu_nccl_sends.restype = L.cuda_emu_nccl_allgathers.restype = ctypes.c_longlong
+            extra = f" sends={L.cuda_emu_nccl_sends()} allgathers={L.cuda_emu_nccl_allgathers()}"
+        print(f"MGPU OK world={world} checks={n_checks}{extra}", flush=True)
     dist.destroy_process_group()
 
 
