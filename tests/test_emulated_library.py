@@ -80,3 +80,35 @@ def test_two_rank_row_slabs_under_emulation(tmp_path, knobs):
         # the communication-avoiding plan really ran: far fewer point-to-point messages than the default schedule
         sends = int(out.stdout.split("sends=")[1].split()[0])
         assert sends < 620, out.stdout[-500:]
+
+
+BENCH_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks"]
+
+
+@pytest.mark.parametrize("world,extra", [(1, []), (2, ["--aggl", "5", "--level", "8"]), (1, ["--smoother", "rbgs", "--gamma", "2"])],
+                         ids=["1rank", "2ranks_slab_host_buffers", "rbgs_wcycle"])
+def test_bench_harness_end_to_end_under_emulation(tmp_path, world, extra):
+    """bench.py's own arm with the REAL Multigrid / C ABI (tests/host_emul/bench_emu_worker.py): the N > 1 leg with
+    slab-sized host buffers included.  Checks the JSON contract, not the numbers."""
+    import json
+    worker = os.path.join(ROOT, "tests", "host_emul", "bench_emu_worker.py")
+    if world == 1:
+        cmd = [sys.executable, worker, "--level", "6", *extra]
+    else:
+        with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), worker, *extra]
+    out = subprocess.run(cmd, cwd=ROOT, env={**ENV, "MGB200_EMU_DIR": str(tmp_path), "OMP_NUM_THREADS": "1"}, capture_output=True,
+                         text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    for k in BENCH_KEYS:
+        assert k in d, k
+    assert d["n_gpus"] == world and d["gpu_launches"] > 0 and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
+    assert d["roofline"]["achieved"] > 0 and set(["bound", "peak", "unit", "frac", "traffic"]) <= set(d["roofline"])
