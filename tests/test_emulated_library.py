@@ -112,3 +112,22 @@ def test_bench_harness_end_to_end_under_emulation(tmp_path, world, extra):
     assert d["n_gpus"] == world and d["gpu_launches"] > 0 and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
     assert d["roofline"]["achieved"] > 0 and set(["bound", "peak", "unit", "frac", "traffic"]) <= set(d["roofline"])
+
+
+def test_smoke_entry_under_emulation():
+    code = ("import sys; sys.path.insert(0, 'tests'); import conftest; conftest.use_emulated_library();"
+            "import __graft_entry__ as g; g.smoke()")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=ENV, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "smoke OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_cpp_driver_example_under_emulation(tmp_path, emulated_library):
+    """examples/poisson_main.cpp (the reference's main() over include/mgb200_driver.hpp) linked against the emulated
+    library: 129^2, V(2,2) solve + FMG."""
+    libdir = os.path.dirname(emulated_library)
+    exe = str(tmp_path / "poisson_main_emu")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "poisson_main.cpp"),
+                    "-o", exe, "-L" + libdir, "-lmgb200_emu", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe, "7", "1", "2"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "Size of finest level solution is 16129" in out.stdout and "Program Running Correctly" in out.stdout
