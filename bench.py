@@ -366,6 +366,25 @@ def run_ours(args, rank, world, local_rank):
         except Exception as ex:  # noqa: BLE001 - informational leg only
             e2e["fullmultigrid_call"] = {"error": str(ex)}
 
+    # N > 1: the same workload on ONE GPU (rank 0 alone, resident data, same flags), so that the strong-scaling
+    # denominator for this grid size is in the same line (bench.py --gpus 1 measures BASELINE configs[1], 4097^2)
+    n1 = None
+    if world > 1 and not args.no_n1:
+        if rank == 0:
+            try:
+                mg1 = mgb200.Multigrid(level, dtype=dtype, smoother=args.smoother, device=local_rank, graph=not args.no_graph,
+                                       fused=not args.no_fused, coarse_tail=not args.no_tail)
+                mg1.force_constant(4.0)
+                mg1.zero_u(level)
+                mg1.time_cycle(level, nu1, nu2, gamma, W)
+                ms1 = mg1.time_cycle(level, nu1, nu2, gamma, K) / K
+                mg1.close()
+                n1 = {"workload": f"{n + 2}^2, same cycle on 1 GPU (rank 0 alone, b = 4h^2)", "ms_per_step": ms1,
+                      "value": upd / (ms1 * 1e-3), "unit": UNIT}
+            except Exception as ex:  # noqa: BLE001 - informational leg only
+                n1 = {"error": str(ex)}
+        barrier()
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if dtype == np.float64 else "f32", "data": "synthetic",
@@ -380,6 +399,8 @@ def run_ours(args, rank, world, local_rank):
                                                                               "coarse_tail": not args.no_tail}},
             "finest_points_per_s": n * n / (ms_step * 1e-3),
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches * 1), "clocks": clocks}
+    if n1 is not None:
+        line["n1_same_workload"] = n1
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_vcycle_rate(level, nu1, nu2, steps=3, warmup=1, with_csr=True)
     mg.close()
@@ -474,6 +495,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--aggl", type=int, default=0, help="agglomeration level for N>1 (0 = library default)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (tuning runs)")
+    ap.add_argument("--no-n1", action="store_true", help="N>1: skip the single-GPU run of the same workload on rank 0")
     ap.add_argument("--micro", action="store_true",
                     help="BASELINE configs[4]: smoother/residual micro-benchmark (default 32769^2; use --dtype f32)")
     ap.add_argument("--full-host-vectors", action="store_true",

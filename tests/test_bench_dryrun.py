@@ -76,7 +76,7 @@ class StubMG:
 
 def _args(**kw):
     d = dict(gpus=1, steps=3, warmup=1, impl="ours", level=6, dtype="f64", smoother="jacobi", nu1=2, nu2=2, gamma=1,
-             no_graph=False, no_fused=False, no_tail=False, no_cpu=True, aggl=0, no_e2e=False, full_host_vectors=False,
+             no_graph=False, no_fused=False, no_tail=False, no_cpu=True, aggl=0, no_e2e=False, full_host_vectors=False, no_n1=False,
              micro=False)
     d.update(kw)
     return argparse.Namespace(**d)
