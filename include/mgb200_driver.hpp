@@ -14,6 +14,9 @@
 //   fullmultigrid(q, a_h, f_h)                      P:629   fullmultigrid(q, a_h, f_h)
 //   globalforcefunction()                           P:283   globalforcefunction(q)
 //   main() level loop                               P:661   queue(finest_level, coarsest_level)
+//   v2 sketch (Multigrid_functions.cpp, M):                 ProblemVar<T>, fullmultigrid(q, obj, f_h, level),
+//     ProblemVar M:16, fullmultigrid M:175, multigrid_solver M:193   multigrid_solver(obj); sampled f / Dirichlet g:
+//                                                           globalforcefunction(q, f, g)
 //
 // Errors: the reference has none; here every failing call throws
 // std::runtime_error carrying mg_last_error().  T is float (as P) or double (as M).
@@ -23,6 +26,7 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <unordered_map>
 #include <vector>
 
 #include "mgb200.h"
@@ -148,6 +152,105 @@ std::vector<T> globalforcefunction(queue<T>& q)
     q.check(mg_force_constant(q.handle(), q.par.f), "globalforcefunction");
     q.check(mg_get_rhs_host(q.handle(), q.par.finest_level, b.data()), "globalforcefunction");
     return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// globalforcefunction generalised from the constant f = 4 with a zero ring (P:123,
+// P:283-335) to a sampled f(x, y) and Dirichlet data g(x, y).  b_i = f(x_i, y_i) h^2 (the lumped P1
+// load of P:175-186); a boundary neighbour contributes +g to its interior node's row, so the device
+// keeps the zero ring and the kernels do not change.  Host-side set-up, like the reference's.
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename F, typename G>
+std::vector<T> globalforcefunction(queue<T>& q, F f, G g)
+{
+    const int N = 1 << q.par.finest_level, n = N - 1;
+    const double h = 1.0 / N;
+    std::vector<T> b((std::size_t)n * n);
+    for (int row = 1; row <= n; ++row)          // row <-> y, P:227-228
+        for (int col = 1; col <= n; ++col) {
+            const double x = col * h, y = row * h;
+            double v = (double)f(x, y) * h * h;
+            if (row == 1) v += (double)g(x, 0.0);
+            if (row == n) v += (double)g(x, 1.0);
+            if (col == 1) v += (double)g(0.0, y);
+            if (col == n) v += (double)g(1.0, y);
+            b[(std::size_t)(row - 1) * n + (col - 1)] = (T)v;
+        }
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the call shape of the reference's second sketch (Multigrid_functions.cpp, "M:"):
+// a problem object with a per-level load-vector dictionary (M:16-26), explicit level arguments, and
+// multigrid_solver(obj) (M:193-197).  Operators are the structured-grid ones of libmgb200; the
+// coarsest level is smoothed (P:583-587), there is no sparse-LU solve (M:63-72: DESIGN.md section 8).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct ProblemVar {
+    parameters par = v2_parameters();
+    std::unordered_map<int, std::vector<T>> b_dict;   // M:22: load vector per level; missing levels are restricted (P:641)
+
+    static parameters v2_parameters()
+    {
+        parameters p;
+        p.finest_level = 5;    // M:45
+        p.coarsest_level = 1;  // M:44 has 0: no unknowns on a structured grid
+        p.mu0 = 2;             // M:46
+        p.mu1 = 1;             // M:47
+        p.mu2 = 1;             // M:48
+        return p;              // omega: M:49 `4 / 5` is integer 0 (erratum); P:127's 2/3 is kept
+    }
+};
+
+// M:75-96: in place, void, explicit level.  (M:87 hard-codes 10 sweeps; here obj.par.mu1.)
+template <typename T>
+void jacobirelaxation(queue<T>& q, std::vector<T>& vec, std::vector<T>& b, ProblemVar<T>& obj, int current_level)
+{
+    q.check(mg_host_jacobirelaxation(q.handle(), current_level, vec.data(), b.data(), obj.par.mu1), "jacobirelaxation");
+}
+
+// M:132-173
+template <typename T>
+std::vector<T> vcyclemultigrid(queue<T>& q, ProblemVar<T>& obj, std::vector<T>& vec_h, std::vector<T>& f_h, int current_level)
+{
+    std::vector<T> out(vec_h);
+    q.check(mg_host_vcyclemultigrid(q.handle(), current_level, out.data(), f_h.data(), obj.par.mu1, obj.par.mu2, obj.par.gamma),
+            "vcyclemultigrid");
+    return out;
+}
+
+// M:175-191: the coarser problem first (its load vector from b_dict, M:183), interpolate (M:185), mu0+1 cycles (M:186-188)
+template <typename T>
+std::vector<T> fullmultigrid(queue<T>& q, ProblemVar<T>& obj, std::vector<T>& f_h, int current_level)
+{
+    mg_ctx* c = q.handle();
+    const int lo = obj.par.coarsest_level;
+    q.check(mg_set_rhs_host(c, current_level, f_h.data()), "fullmultigrid: f_h");
+    for (int l = current_level - 1; l >= lo; --l) {
+        auto it = obj.b_dict.find(l);
+        if (it != obj.b_dict.end()) q.check(mg_set_rhs_host(c, l, it->second.data()), "fullmultigrid: b_dict");
+        else q.check(mg_restrict_rhs(c, l + 1), "fullmultigrid: restrict");
+    }
+    q.check(mg_zero_u(c, lo), "fullmultigrid");                                              // M:176
+    for (int i = 0; i <= obj.par.mu0; ++i) q.check(mg_cycle(c, lo, obj.par.mu1, obj.par.mu2, 1), "fullmultigrid");
+    for (int l = lo + 1; l <= current_level; ++l) {
+        q.check(mg_prolong_set(c, l), "fullmultigrid: interpolation");                       // M:185
+        for (int i = 0; i <= obj.par.mu0; ++i) q.check(mg_cycle(c, l, obj.par.mu1, obj.par.mu2, 1), "fullmultigrid");
+    }
+    const std::size_t n = (std::size_t)mg_level_side(current_level);
+    std::vector<T> vec_h(n * n, 0);
+    q.check(mg_get_u_host(c, current_level, vec_h.data()), "fullmultigrid: result");
+    return vec_h;
+}
+
+// M:193-197
+template <typename T>
+std::vector<T> multigrid_solver(ProblemVar<T>& obj)
+{
+    queue<T> q(obj.par);
+    auto it = obj.b_dict.find(obj.par.finest_level);
+    if (it == obj.b_dict.end()) throw std::runtime_error("multigrid_solver: b_dict has no finest-level load vector");
+    return fullmultigrid(q, obj, it->second, obj.par.finest_level);
 }
 
 }  // namespace mgb200

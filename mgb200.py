@@ -11,4 +11,8 @@ _pkg = importlib.import_module("multigrid_nikhil_c-_b200")
 capi = _pkg.capi
 Multigrid = _pkg.Multigrid
 comm_id = _pkg.comm_id
+ProblemVar = _pkg.ProblemVar
+load_vector = _pkg.load_vector
+multigrid_solver = _pkg.multigrid_solver
+problem = _pkg.problem
 package = _pkg

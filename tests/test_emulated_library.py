@@ -52,7 +52,7 @@ def test_emulation_really_loads_the_emulated_library():
 def test_gpu_parity_suite_under_emulation():
     """test_parity_gpu.py minus the 1025^2 / 4097^2 cases and the C++ example (which links the real library)."""
     out = child_pytest(["tests/test_parity_gpu.py", "-k",
-                        "not 4097 and not cpp_driver and not combinations[9- and not 10-float and not iterates_bitwise[9"])
+                        "not 4097 and not cpp_ and not combinations[9- and not 10-float and not iterates_bitwise[9"])
     assert " passed" in out and "failed" not in out
 
 
@@ -133,3 +133,18 @@ def test_cpp_driver_example_under_emulation(tmp_path, emulated_library):
     out = subprocess.run([exe, "7", "1", "2"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "Size of finest level solution is 16129" in out.stdout and "Program Running Correctly" in out.stdout
+
+
+def test_problemvar_example_under_emulation(tmp_path, emulated_library):
+    """examples/problemvar_main.cpp: multigrid_solver(ProblemVar&) (M:193) on a Dirichlet problem with a sampled f."""
+    libdir = os.path.dirname(emulated_library)
+    exe = str(tmp_path / "problemvar_main_emu")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "problemvar_main.cpp"),
+                    "-o", exe, "-L" + libdir, "-lmgb200_emu", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe, "6"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "max |u - (x^2+y^2)|" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_problem_setup_gpu_tests_under_emulation():
+    out = child_pytest(["tests/test_problem_setup.py"])
+    assert " passed" in out and "failed" not in out

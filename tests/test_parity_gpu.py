@@ -238,3 +238,17 @@ def test_cpp_driver_example_runs_like_the_reference_main(mgb, tmp_path):
     # FMG with one V(2,2) per level (mu0 = 0): the discrete solution is within 2% in the max norm
     umax = float(out.stdout.split("max u = ")[1].split()[0])
     assert abs(umax - 0.2946818) < 0.01
+
+
+def test_cpp_problemvar_example(mgb, tmp_path):
+    """examples/problemvar_main.cpp: the v2 call shape multigrid_solver(ProblemVar&) (M:193-197) with a sampled
+    right-hand side and Dirichlet data; exact solution x^2 + y^2."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "multigrid_nikhil_c-_b200", "lib")
+    exe = str(tmp_path / "problemvar_main")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "examples", "problemvar_main.cpp"), "-o", exe, "-L" + libdir, "-lmgb200",
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe, "8"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "max |u - (x^2+y^2)|" in out.stdout, out.stdout + out.stderr
