@@ -254,9 +254,24 @@ static void run_group(dim3 grid, dim3 block, size_t smem, unsigned first_cta, un
     Group* saved_group = g_group;
     g_group = &grp;
     size_t live = grp.fibers.size();
+    // CUDA_EMU_ORDER = forward (default) | reverse | random: the order in which runnable threads are resumed between
+    // barriers.  A kernel without data races gives the same bits under every order; a missing barrier does not.
+    static const int order_mode = []() {
+        const char* e = getenv("CUDA_EMU_ORDER");
+        return !e ? 0 : (!std::strcmp(e, "reverse") ? 1 : (!std::strcmp(e, "random") ? 2 : 0));
+    }();
+    static unsigned long long rng_state = 0x9E3779B97F4A7C15ULL;
+    std::vector<unsigned> order(grp.fibers.size());
+    for (unsigned i = 0; i < order.size(); ++i) order[i] = order_mode == 1 ? (unsigned)(order.size() - 1 - i) : i;
     while (live > 0) {
         bool progress = false;
-        for (Fiber& f : grp.fibers) {
+        if (order_mode == 2)
+            for (size_t i = order.size(); i > 1; --i) {   // Fisher-Yates with xorshift64
+                rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17;
+                std::swap(order[i - 1], order[rng_state % i]);
+            }
+        for (unsigned idx : order) {
+            Fiber& f = grp.fibers[idx];
             if (f.done) continue;
             if (f.wait_bar) {
                 if (f.wait_bar->gen == f.wait_gen) continue;
