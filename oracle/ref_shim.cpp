@@ -119,6 +119,21 @@ void ref_jacobirelaxation(int level, float* v_inout, const float* f, int mu)
     std::memcpy(v_inout, r.data(), r.size() * sizeof(float));
 }
 
+// The reference's OWN jacobirelaxation body (P:125-147: gemv with alpha = -omega/4, two scal, two add) on a
+// caller-supplied CSR operator -- the tests hand it the INTENDED off-diagonal part (A_lu = -1 per grid neighbour,
+// SURVEY App. B) instead of the as-written one (all zeros, E1), which pins the smoother's algebra, its omega and
+// its in-place / return behaviour against the oracle.
+void ref_jacobirelaxation_with(int n, int* row_ptr, int* col_ind, float* val, float* v_inout, const float* f, int mu)
+{
+    matrix_handle_t h;
+    init_matrix_handle(&h);
+    set_csr_data(h, n, n, oneapi::mkl::index_base::zero, row_ptr, col_ind, val);
+    std::vector<float> v(v_inout, v_inout + n), fh(f, f + n);
+    std::vector<float> r = jacobirelaxation(g_q, h, n, v, fh, mu);
+    std::memcpy(v_inout, r.data(), r.size() * sizeof(float));   // r is a copy of the mutated v (P:146)
+    delete h;
+}
+
 // the whole program: main()'s last lines P:725-727.  ~20-30 s single thread.
 long long ref_run_program(float* solution_out)
 {

@@ -66,6 +66,25 @@ for lvl in (8, 9):
     R.ref_counters(c)
     pins["vcycle_calls"][f"L{lvl}"] = {"gemv": c[0], "scal": c[1], "add": c[2], "sub": c[3], "u_min": float(u.min()),
                                        "u_max": float(u.max())}
+# jacobirelaxation (P:125-147), the reference's own body, on the INTENDED off-diagonal operator (A_lu = -1 per neighbour)
+def intended_a_lu(m):
+    rp, ci = [0], []
+    for r in range(m):
+        for c in range(m):
+            for rr, cc in ((r - 1, c), (r, c - 1), (r, c + 1), (r + 1, c)):
+                if 0 <= rr < m and 0 <= cc < m:
+                    ci.append(rr * m + cc)
+            rp.append(len(ci))
+    return np.array(rp, np.int32), np.array(ci, np.int32), np.full(len(ci), -1.0, np.float32)
+
+
+for m, mu in ((7, 1), (15, 3), (31, 10)):
+    rp, ci, va = intended_a_lu(m)
+    v = np.random.default_rng(2000 + m).uniform(-1, 1, m * m).astype(np.float32)
+    fh = (1e-2 * np.random.default_rng(3000 + m).uniform(-1, 1, m * m)).astype(np.float32)
+    arrays[f"jacobi_v_{m}"], arrays[f"jacobi_f_{m}"] = v.copy(), fh
+    R.ref_jacobirelaxation_with(m * m, P(rp), P(ci), P(va), P(v), P(fh), mu)
+    arrays[f"jacobi_out_{m}_mu{mu}"] = v
 # the whole program as written
 t0 = time.time()
 sol = np.zeros(n * n, np.float32)

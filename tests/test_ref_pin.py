@@ -50,6 +50,47 @@ def test_interpolation2d_live_reference(orc, ref):
         assert np.array_equal(out, orc.interpolation2d(x)), m
 
 
+def _intended_a_lu(m):
+    rp, ci = [0], []
+    for r in range(m):
+        for c in range(m):
+            for rr, cc in ((r - 1, c), (r, c - 1), (r, c + 1), (r + 1, c)):
+                if 0 <= rr < m and 0 <= cc < m:
+                    ci.append(rr * m + cc)
+            rp.append(len(ci))
+    return np.array(rp, np.int32), np.array(ci, np.int32), np.full(len(ci), -1.0, np.float32)
+
+
+def test_jacobirelaxation_matches_the_references_own_body_on_the_intended_operator(orc):
+    """P:125-147 (gemv alpha = -omega/4, scal (1-omega), scal omega/4, two adds; omega = 2/3 P:127) executed by the
+    reference's own function on A_lu = -1 per neighbour.  The oracle sums the four neighbours as (N+S)+(W+E), the CSR
+    row sum runs N, W, E, S: same algebra, different association => a few fp32 ulps per sweep, not bits."""
+    for m, mu in ((7, 1), (15, 3), (31, 10)):
+        v, fh, want = INTERP[f"jacobi_v_{m}"], INTERP[f"jacobi_f_{m}"], INTERP[f"jacobi_out_{m}_mu{mu}"]
+        got = orc.jacobirelaxation(v, fh, mu)
+        assert np.abs(got - want).max() <= 4e-7 * mu * np.abs(want).max(), (m, mu, np.abs(got - want).max())
+        # and it is NOT some other smoother: one sweep moves v by far more than the tolerance
+        assert np.abs(orc.jacobirelaxation(v, fh, mu + 1) - want).max() > 1e-3
+        # the oracle's reference-STRUCTURED path (CSR SpMV + scal/add passes, bench.py's CPU baseline A) reproduces the
+        # reference's function bit for bit
+        lvl = int(np.log2(m + 1))
+        h = orc.csr_build(lvl, np.float32)
+        try:
+            assert np.array_equal(orc.csr_jacobirelaxation(h, v, fh, mu), want), (m, mu)
+        finally:
+            orc.csr_free(h, np.float32)
+
+
+def test_jacobirelaxation_live_reference(orc, ref):
+    m, mu = 23, 4
+    rp, ci, va = _intended_a_lu(m)
+    v = np.random.default_rng(11).uniform(-1, 1, m * m).astype(np.float32)
+    fh = (1e-2 * np.random.default_rng(12).uniform(-1, 1, m * m)).astype(np.float32)
+    out = v.copy()
+    ref.ref_jacobirelaxation_with(m * m, P(rp), P(ci), P(va), P(out), P(fh), mu)
+    assert np.abs(orc.jacobirelaxation(v, fh, mu) - out).max() <= 4e-7 * mu * np.abs(out).max()
+
+
 def test_restriction_weight_as_written_is_zero_and_adjoint_pins_the_stencil(orc):
     """E2: `(1 / 16)` at P:539 is integer 0, so the reference's restriction2d returns zeros and
     cannot pin the stencil directly.  The stencil is pinned through P = 4 R^T against the
