@@ -81,7 +81,7 @@ def _digest() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     stamp = os.path.join(BUILD, "stamp")
-    dig = _digest()
+    dig = _digest() + os.environ.get("CUDA_EMU_UBSAN", "")
     if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == dig:
         return OUT
     src_dir = os.path.join(BUILD, "pkg", "csrc")     # same depth as the real csrc: "../../include/mgb200.h" resolves
@@ -95,6 +95,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with open(os.path.join(src_dir, out_name), "w") as f:
             f.write(rewrite(open(p).read(), base))
     flags = ["-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-fno-strict-aliasing", "-w", "-DMGB_EMU=1", "-I" + EMU]
+    # CUDA_EMU_UBSAN=1: alignment / bounds / integer-overflow checks in every kernel and host function (a misaligned
+    # 16-byte vector access is a fault on the GPU but usually silent on x86)
+    san = os.environ.get("CUDA_EMU_UBSAN") == "1"
+    if san:
+        flags += ["-fsanitize=alignment,bounds,signed-integer-overflow,shift,null", "-fno-sanitize-recover=all", "-g"]
     objs, procs = [], []
     for u in UNITS + ["emu_runtime.cpp"]:
         src = os.path.join(EMU, u) if u == "emu_runtime.cpp" else os.path.join(src_dir, u[:-3] + ".cpp")
@@ -107,7 +112,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"emulation build of {u} failed:\n{out[-6000:]}")
         if verbose and out:
             print(out)
-    link = subprocess.run(["g++", "-shared", "-o", OUT, *objs, "-ldl"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    link = subprocess.run(["g++", "-shared", "-o", OUT, *objs, "-ldl", *(["-fsanitize=undefined"] if san else [])], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if link.returncode != 0:
         raise RuntimeError("emulation link failed:\n" + link.stdout[-4000:])
     with open(stamp, "w") as f:
