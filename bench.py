@@ -394,11 +394,15 @@ def run_ours(args, rank, world, local_rank):
                        "level": level, "rhs": "h^2*U(-1,1) rng(1234)" if not slab else "h^2*U(-1,1), rng seeded per row slab", "updates_per_cycle": upd,
                        "l2_policy": "inputs larger than L2 (4 arrays x %.0f MB on the finest level)" % (n * n * esize / 1e6),
                        "regions": regions, "region_stat": "median", "agglomerate_level": mg.info(capi.MG_INFO_AGGLOMERATE_LEVEL, level) if world > 1 else None,
-                       "flags": {"graph": not args.no_graph,
+                       "timed_as": f"{K} consecutive cycles per region through mg_time_cycle (mg_cycles)",
+                       "flags": {"visit_chain": os.environ.get("MGB200_CHAIN") == "1", "graph": not args.no_graph,
                                                                               "fused": not args.no_fused,
                                                                               "coarse_tail": not args.no_tail}},
             "finest_points_per_s": n * n / (ms_step * 1e-3),
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches * 1), "clocks": clocks}
+    if os.environ.get("MGB200_CHAIN") == "1":
+        # with visit chains the K timed cycles share POST+PRE launches on the finest level; also report one isolated cycle
+        line["isolated_cycle_ms"] = statistics.median([mg.time_cycle(level, nu1, nu2, gamma, 1) for _ in range(20)])
     if n1 is not None:
         line["n1_same_workload"] = n1
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -95,6 +95,7 @@ def lib() -> ctypes.CDLL:
         "mg_prolong_correct": (ci, [vp, ci]),
         "mg_prolong_set": (ci, [vp, ci]),
         "mg_cycle": (ci, [vp, ci, ci, ci, ci]),
+        "mg_cycles": (ci, [vp, ci, ci, ci, ci, ci]),
         "mg_fmg": (ci, [vp, ci, ci, ci]),
         "mg_solve": (ci, [vp, cd, ci, ci, ci, ci, ctypes.POINTER(ci), ctypes.POINTER(cd), vp]),
         "mg_host_jacobirelaxation": (ci, [vp, ci, vp, vp, ci]),

@@ -177,6 +177,14 @@ int mg_cycle(mg_ctx* c, int level, int nu1, int nu2, int gamma)
     return guarded(c, [&](Ctx& x) { x.cycle(level, nu1, nu2, gamma); });
 }
 
+int mg_cycles(mg_ctx* c, int level, int nu1, int nu2, int gamma, int count)
+{
+    return guarded(c, [&](Ctx& x) {
+        MG_REQUIRE(count >= 0, "count >= 0 required");
+        x.cycles(level, nu1, nu2, gamma, count);
+    });
+}
+
 int mg_fmg(mg_ctx* c, int cycles, int nu1, int nu2) { return guarded(c, [&](Ctx& x) { x.fmg(cycles, nu1, nu2); }); }
 
 int mg_solve(mg_ctx* c, double rtol, int max_cycles, int nu1, int nu2, int gamma, int* cycles_out,
@@ -274,7 +282,7 @@ int mg_time_cycle(mg_ctx* c, int level, int nu1, int nu2, int gamma, int reps, f
         MG_CK(cudaEventCreate(&e0));
         MG_CK(cudaEventCreate(&e1));
         MG_CK(cudaEventRecord(e0, x.stream));
-        for (int i = 0; i < reps; ++i) x.cycle(level, nu1, nu2, gamma);
+        x.cycles(level, nu1, nu2, gamma, reps);
         MG_CK(cudaEventRecord(e1, x.stream));
         MG_CK(cudaEventSynchronize(e1));
         MG_CK(cudaEventElapsedTime(ms_out, e0, e1));

@@ -140,6 +140,8 @@ Ctx::Ctx(const mg_config& c) : cfg(c)
     {
         const char* zg = getenv("MGB200_ZERO_GUESS");
         zero_guess = zg && zg[0] == '1';
+        const char* ch = getenv("MGB200_CHAIN");
+        chain = ch && ch[0] == '1';
     }
     fused_setup(*this);
     MG_CK(cudaStreamSynchronize(stream));
@@ -431,20 +433,35 @@ void Ctx::cycle_rec(int level, int nu1, int nu2, int gamma)
     residual(level, false, true);                           // P:604-608
     restrict_to(level, false);                              // P:611, P:613
     const int reps = (level - 1 <= cfg.coarsest_level) ? 1 : std::max(1, gamma);
-    for (int g = 0; g < reps; ++g) cycle_rec(level - 1, nu1, nu2, gamma);  // P:617
+    cycle_rec_visits(level - 1, nu1, nu2, gamma, reps);     // P:617
     prolong(level, true);                                   // P:620-624
     smooth(level, nu2);                                     // P:625
 }
 
-void Ctx::cycle(int level, int nu1, int nu2, int gamma)
+// `visits` consecutive visits of one level (same right-hand side, the iterate carries over): the gamma recursive
+// calls of P:617 for a W-cycle, or consecutive cycles on the top level (P:646-648)
+void Ctx::cycle_rec_visits(int level, int nu1, int nu2, int gamma, int visits)
+{
+    if (visits > 1 && chain && fused_cycle_chain(*this, level, nu1, nu2, gamma, visits)) return;
+    for (int v = 0; v < visits; ++v) cycle_rec(level, nu1, nu2, gamma);
+}
+
+// `count` consecutive cycles from `level`, replayed as ONE CUDA graph when MG_GRAPH is set (cache key: level, sweep
+// counts, cycle index, count and the host state the capture depends on)
+void Ctx::cycles(int level, int nu1, int nu2, int gamma, int count)
 {
     L(level);
-    MG_REQUIRE(nu1 >= 0 && nu2 >= 0 && gamma >= 1, "nu1, nu2 >= 0 and gamma >= 1 required");
-    if (!(cfg.flags & MG_GRAPH) || capturing || (cfg.world > 1 && !graph_dist)) {
-        cycle_rec(level, nu1, nu2, gamma);
+    MG_REQUIRE(nu1 >= 0 && nu2 >= 0 && gamma >= 1 && gamma < 1000, "nu1, nu2 >= 0 and 1 <= gamma < 1000 required");
+    if (count <= 0) return;
+    if (count > 1 && !chain) {   // nothing to fuse across cycles: one (cached) graph per cycle
+        for (int i = 0; i < count; ++i) cycles(level, nu1, nu2, gamma, 1);
         return;
     }
-    auto key = std::make_tuple(level, nu1, nu2, gamma, state_blob());
+    if (!(cfg.flags & MG_GRAPH) || capturing || (cfg.world > 1 && !graph_dist)) {
+        cycle_rec_visits(level, nu1, nu2, gamma, count);
+        return;
+    }
+    auto key = std::make_tuple(level, nu1, nu2, gamma + 1000 * count, state_blob());
     auto it = graphs.find(key);
     if (it == graphs.end()) {
         fused_pretune(*this, level, nu1, nu2, gamma);
@@ -454,7 +471,7 @@ void Ctx::cycle(int level, int nu1, int nu2, int gamma)
         MG_CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         capturing = true;
         try {
-            cycle_rec(level, nu1, nu2, gamma);
+            cycle_rec_visits(level, nu1, nu2, gamma, count);
         } catch (...) {
             capturing = false;
             cudaStreamEndCapture(stream, &g);
@@ -477,15 +494,17 @@ void Ctx::cycle(int level, int nu1, int nu2, int gamma)
     set_state(it->second.state_after);
 }
 
+void Ctx::cycle(int level, int nu1, int nu2, int gamma) { cycles(level, nu1, nu2, gamma, 1); }
+
 void Ctx::fmg(int cycles, int nu1, int nu2)
 {
     MG_REQUIRE(cycles >= 1, "cycles_per_level >= 1 required");
     for (int l = cfg.finest_level; l > cfg.coarsest_level; --l) restrict_to(l, true);  // P:641
     zero_u(cfg.coarsest_level);                                                          // P:630
-    for (int i = 0; i < cycles; ++i) cycle(cfg.coarsest_level, nu1, nu2, 1);             // P:635-637
+    this->cycles(cfg.coarsest_level, nu1, nu2, 1, cycles);                               // P:635-637
     for (int l = cfg.coarsest_level + 1; l <= cfg.finest_level; ++l) {
         prolong(l, false);                                                               // P:645
-        for (int i = 0; i < cycles; ++i) cycle(l, nu1, nu2, 1);                          // P:646-648
+        this->cycles(l, nu1, nu2, 1, cycles);                                            // P:646-648
     }
 }
 

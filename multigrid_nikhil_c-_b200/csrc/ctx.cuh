@@ -93,6 +93,7 @@ struct Ctx {
     bool graph_dist = false;  // capture NCCL exchanges into cycle graphs (MGB200_GRAPH_DIST=1)
     bool zero_guess = false;  // skip reading / writing the zero coarse guess (MGB200_ZERO_GUESS=1)
     bool comm_avoid = false;  // communication-avoiding slab schedule (MGB200_COMM_AVOID=1, csrc/sched.h)
+    bool chain = false;       // fuse POST of one visit of a level with PRE of the next (MGB200_CHAIN=1, stream.cuh MODE_POSTPRE)
 
     explicit Ctx(const mg_config& c);
     ~Ctx();
@@ -116,7 +117,9 @@ struct Ctx {
 
     // cycles
     void cycle(int level, int nu1, int nu2, int gamma);
+    void cycles(int level, int nu1, int nu2, int gamma, int count);   // `count` consecutive cycles (P:646-648 loop)
     void cycle_rec(int level, int nu1, int nu2, int gamma);
+    void cycle_rec_visits(int level, int nu1, int nu2, int gamma, int visits);   // consecutive visits of one level
     void fmg(int cycles, int nu1, int nu2);
     int solve(double rtol, int max_cycles, int nu1, int nu2, int gamma, double* relres, double* history);
     float time_op(int op, int level, int reps);

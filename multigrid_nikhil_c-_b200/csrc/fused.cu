@@ -131,6 +131,16 @@ static StreamArgs<T> make_args(Ctx& ctx, Level& lv, Level* lcv, int ry, int ya =
         a.Nc = lcv->N;
         a.crow_lo = lcv->st_lo;
         a.crow_hi = lcv->st_hi;
+    } else if (MODE == MODE_POSTPRE) {
+        // reads the coarse correction from the current coarse buffer and writes the next visit's zero guess into
+        // the OTHER one (chunks run concurrently: the buffer being read must not be cleared under them)
+        a.ec = (const T*)lcv->u[lcv->cur];
+        a.fc = (T*)lcv->f;
+        a.uc = write_zero_guess ? (T*)lcv->u[lcv->cur ^ 1] : nullptr;
+        a.pitch_c = lcv->pitch;
+        a.Nc = lcv->N;
+        a.crow_lo = lcv->st_lo;
+        a.crow_hi = lcv->st_hi;
     }
     return a;
 }
@@ -473,6 +483,58 @@ static void post_fused(Ctx& ctx, Level& lv, Level& lcv, int nu2)
 }
 
 // ---------------------------------------------------------------------------------
+// visit chains (opt-in MGB200_CHAIN=1): when a level is visited several times in a row on the same right-hand
+// side -- consecutive cycles on the top level (fullmultigrid runs mu0+1 per level, P:646-648; mg_cycles), the gamma
+// visits of a W-cycle on every level below -- POST of visit v and PRE of visit v+1 are ONE streaming launch
+// (stream.cuh MODE_POSTPRE): 3.5 S bytes per point instead of 6.5 S, the iterate between them never goes to memory.
+// ---------------------------------------------------------------------------------
+static int postpre_ns(const Ctx& ctx, const Level& lv, int nu1, int nu2)
+{
+    if (!ctx.chain || !(ctx.cfg.flags & MG_FUSED) || lv.distributed || use_tile(lv)) return 0;
+    if (nu1 < 1 || nu2 < 1 || nu1 > 2 || nu2 > 2) return 0;
+    if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) return nu1 + nu2;          // 2, 3 or 4 pipeline stages
+    return (nu1 == 1 && nu2 == 1) ? 4 : 0;                               // RB-GS: one stage per colour
+}
+
+template <typename T, int NS, bool RBGS>
+static void launch_postpre(Ctx& ctx, Level& lv, Level& lcv, bool write_zero_guess)
+{
+    typedef StreamCfg<T, NS, MODE_POSTPRE> C;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MG_CK(cudaFuncSetAttribute(k_stream<T, NS, MODE_POSTPRE, RBGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)std::max<size_t>(C::SMEM_BYTES, 100 * 1024)));
+        attr_set = true;
+    }
+    ctx.materialize_u(lv);
+    ctx.materialize_u(lcv);
+    const int ry = tuned_ry<T, NS, MODE_POSTPRE, RBGS>(ctx, lv, &lcv);
+    const StreamArgs<T> a = make_args<T, NS, MODE_POSTPRE>(ctx, lv, &lcv, ry, -1, -1, write_zero_guess);
+    raw_launch<T, NS, MODE_POSTPRE, RBGS>(ctx, a);
+    lv.cur ^= 1;
+    lv.hv_u = 0;
+    if (write_zero_guess) {
+        lcv.cur ^= 1;            // the zero guess went into the other coarse buffer
+        lcv.u_zero = false;
+    } else {
+        lcv.u_zero = true;       // zero-guess chain: the child's first kernel does not read its iterate
+    }
+}
+
+template <typename T>
+static void postpre_fused(Ctx& ctx, Level& lv, Level& lcv, int ns, int nu1)
+{
+    const bool wz = !child_takes_zero_guess(ctx, lv, nu1);
+    if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) {
+        if (ns == 2) launch_postpre<T, 2, false>(ctx, lv, lcv, wz);
+        else if (ns == 3) launch_postpre<T, 3, false>(ctx, lv, lcv, wz);
+        else launch_postpre<T, 4, false>(ctx, lv, lcv, wz);
+    } else {
+        launch_postpre<T, 4, true>(ctx, lv, lcv, wz);
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // coarse tail: levels <= tail_top run in ONE launch, entirely in one CTA's shared memory
 // ---------------------------------------------------------------------------------
 static int tail_top(const Ctx& ctx)
@@ -697,9 +759,33 @@ bool fused_cycle_level(Ctx& ctx, int level, int nu1, int nu2, int gamma)
     if (ctx.f64()) pre_fused<double>(ctx, lv, lcv, nu1);
     else pre_fused<float>(ctx, lv, lcv, nu1);
     const int reps = (level - 1 <= ctx.cfg.coarsest_level) ? 1 : std::max(1, gamma);
-    for (int g = 0; g < reps; ++g) ctx.cycle_rec(level - 1, nu1, nu2, gamma);
+    ctx.cycle_rec_visits(level - 1, nu1, nu2, gamma, reps);
     if (ctx.f64()) post_fused<double>(ctx, lv, lcv, nu2);
     else post_fused<float>(ctx, lv, lcv, nu2);
+    return true;
+}
+
+bool fused_cycle_chain(Ctx& ctx, int level, int nu1, int nu2, int gamma, int visits)
+{
+    if (visits < 2 || level <= ctx.cfg.coarsest_level) return false;
+    if (level == ctail_top(ctx) || level == tail_top(ctx)) return false;   // one launch per visit already
+    Level& lv = ctx.L(level);
+    Level& lcv = ctx.L(level - 1);
+    const int ns = postpre_ns(ctx, lv, nu1, nu2);
+    if (ns == 0) return false;
+    if (ctx.f64()) pre_fused<double>(ctx, lv, lcv, nu1);
+    else pre_fused<float>(ctx, lv, lcv, nu1);
+    const int reps = (level - 1 <= ctx.cfg.coarsest_level) ? 1 : std::max(1, gamma);
+    for (int v = 0; v < visits; ++v) {
+        ctx.cycle_rec_visits(level - 1, nu1, nu2, gamma, reps);
+        if (v + 1 < visits) {
+            if (ctx.f64()) postpre_fused<double>(ctx, lv, lcv, ns, nu1);
+            else postpre_fused<float>(ctx, lv, lcv, ns, nu1);
+        } else {
+            if (ctx.f64()) post_fused<double>(ctx, lv, lcv, nu2);
+            else post_fused<float>(ctx, lv, lcv, nu2);
+        }
+    }
     return true;
 }
 
@@ -718,7 +804,14 @@ static void pretune_t(Ctx& ctx, int level, int nu1, int nu2)
             if (k1 == 2) tuned_ry<T, 2, MODE_PRE, false>(ctx, lv, &lcv); else if (k1 == 1) tuned_ry<T, 1, MODE_PRE, false>(ctx, lv, &lcv);
             if (k2 == 2) tuned_ry<T, 2, MODE_POST, false>(ctx, lv, &lcv); else if (k2 == 1) tuned_ry<T, 1, MODE_POST, false>(ctx, lv, &lcv);
             if (nu1 - k1 >= 3 || nu2 - k2 >= 3) tuned_ry<T, 3, MODE_SWEEPS, false>(ctx, lv, nullptr);
+            switch (postpre_ns(ctx, lv, nu1, nu2)) {
+                case 2: tuned_ry<T, 2, MODE_POSTPRE, false>(ctx, lv, &lcv); break;
+                case 3: tuned_ry<T, 3, MODE_POSTPRE, false>(ctx, lv, &lcv); break;
+                case 4: tuned_ry<T, 4, MODE_POSTPRE, false>(ctx, lv, &lcv); break;
+                default: break;
+            }
         } else {
+            if (postpre_ns(ctx, lv, nu1, nu2) == 4) tuned_ry<T, 4, MODE_POSTPRE, true>(ctx, lv, &lcv);
             if (k1 == 2) tuned_ry<T, 4, MODE_PRE, true>(ctx, lv, &lcv); else if (k1 == 1) tuned_ry<T, 2, MODE_PRE, true>(ctx, lv, &lcv);
             if (k2 == 2) tuned_ry<T, 4, MODE_POST, true>(ctx, lv, &lcv); else if (k2 == 1) tuned_ry<T, 2, MODE_POST, true>(ctx, lv, &lcv);
             if (nu1 - k1 >= 2 || nu2 - k2 >= 2) tuned_ry<T, 4, MODE_SWEEPS, true>(ctx, lv, nullptr);

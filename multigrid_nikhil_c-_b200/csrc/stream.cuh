@@ -15,6 +15,10 @@
 //   SWEEPS: u_out = S^NS u                               3 S B/pt per launch (not per sweep)
 //   PRE   : u_out = S^NS u;  f_c = R (f - A u_out); u_c = 0     (3 + 1/4 [+1/4]) S B/pt
 //   POST  : u_out = S^NS (u + P e_c)                            (3 + 1/4) S B/pt
+//   POSTPRE: POST of one visit of a level fused with PRE of the NEXT visit of the same level (consecutive cycles on
+//            the finest level -- fullmultigrid runs mu0+1 of them per level, P:646-648 -- and the gamma visits of a
+//            W-cycle):  u_out = S^(nu2+nu1) (u + P e_c);  f_c = R (f - A u_out);  u_c = 0      (3 + 1/2) S B/pt
+//            instead of 6.5 S for POST + PRE: the iterate between the two visits never goes to memory.
 //
 // S is one weighted-Jacobi sweep, or one *half* sweep (one colour) of red-black
 // Gauss-Seidel (then NS = 2 x sweeps).  Every point value is produced by the same
@@ -37,7 +41,10 @@
 
 namespace mgb {
 
-enum { MODE_SWEEPS = 0, MODE_PRE = 1, MODE_POST = 2 };
+enum { MODE_SWEEPS = 0, MODE_PRE = 1, MODE_POST = 2,
+       MODE_POSTPRE = 3 };   // POST of one level visit fused with PRE of the next visit of the same level (see below)
+constexpr bool mode_has_post(int m) { return m == MODE_POST || m == MODE_POSTPRE; }   // stage 0 adds the coarse correction
+constexpr bool mode_has_pre(int m) { return m == MODE_PRE || m == MODE_POSTPRE; }     // residual + full weighting after stage NS
 
 constexpr int kStreamWarps = 1;  // warps (independent work items) per CTA.  4 lock-stepped warps per CTA (bar.sync every 3 rows)
                                  // were measured slower and more erratic (profiles/r01_tune_stream.txt)
@@ -46,20 +53,21 @@ constexpr int kRingSlots = 12;   // 4 blocks x 3 slots
 template <typename T, int NS, int MODE>
 struct StreamCfg {
     static constexpr int V = Vec<T>::N;
-    static constexpr int HL = NS + (MODE == MODE_PRE ? 2 : 0);                          // columns needed to the left
-    static constexpr int HR = NS + (MODE == MODE_PRE ? 1 : (MODE == MODE_POST ? 1 : 0));  // ... to the right
+    static constexpr bool HAS_POST = mode_has_post(MODE), HAS_PRE = mode_has_pre(MODE);
+    static constexpr int HL = NS + (HAS_PRE ? 2 : 0);                                   // columns needed to the left
+    static constexpr int HR = NS + (HAS_PRE ? 1 : 0) + (HAS_POST ? 1 : 0);              // ... to the right
     static constexpr int HMAX = HL > HR ? HL : HR;
     static constexpr int HLANES = (HMAX + V - 1) / V;                                   // halo lanes per side
     static constexpr int OUTW = 32 * V - 2 * V * HLANES;                                // output columns per strip
-    static constexpr int HT = NS + (MODE == MODE_PRE ? 2 : (MODE == MODE_POST ? 1 : 0));  // rows needed above
-    static constexpr int HB = NS + (MODE == MODE_PRE ? 2 : 0);                          // rows needed below
+    static constexpr int HT = NS + (HAS_PRE ? 2 : 0) + (HAS_POST ? 1 : 0);              // rows needed above
+    static constexpr int HB = NS + (HAS_PRE ? 2 : 0);                                   // rows needed below
     static constexpr int DEPTH = kRingSlots;
     static constexpr int D = DEPTH - NS - 3;                                            // prefetch distance (rows)
-    static constexpr int NW = NS + (MODE == MODE_PRE ? 1 : 0);                          // register windows of u_s
+    static constexpr int NW = NS + (HAS_PRE ? 1 : 0);                                   // register windows of u_s
     // slot: [u: 32 V][f: 32 V]; POST keeps the coarse rows in a second, half-rate ring
     static constexpr int SLOT_ELEMS = 32 * V * 2;
     static constexpr int CSLOT_ELEMS = 32 * (V / 2);
-    static constexpr int WARP_ELEMS = DEPTH * SLOT_ELEMS + (MODE == MODE_POST ? DEPTH * CSLOT_ELEMS : 0);
+    static constexpr int WARP_ELEMS = DEPTH * SLOT_ELEMS + (HAS_POST ? DEPTH * CSLOT_ELEMS : 0);
     static constexpr size_t SMEM_BYTES = (size_t)kStreamWarps * WARP_ELEMS * sizeof(T);
     static_assert(D >= 3, "ring too shallow");
 };
@@ -175,7 +183,7 @@ struct Streamer {
         cp_async16(dst + 32 * V, v ? g_f : safe_f, v);
         g_u += a.pitch;
         g_f += a.pitch;
-        if (MODE == MODE_POST) {
+        if (C::HAS_POST) {
             // coarse row ceil(y/2): a new one starts at every odd y; even rows re-read the previous one (L1 hit)
             const int ic = (y + 1) >> 1;
             const bool vc = lane_ldc && (ic >= a.crow_lo) && (ic < a.crow_hi) && (y >= 0);
@@ -222,7 +230,7 @@ struct Streamer {
         } else {
             ldv<T>(rslot<PH, 0>(), cur);
         }
-        if (MODE == MODE_POST) {
+        if (C::HAS_POST) {
             T ca[H + 1], cb[H + 1], e[V];
             const T* pa = cslot<PH, 0>();
 #pragma unroll
@@ -286,7 +294,7 @@ struct Streamer {
         }
 
         // ---- PRE: residual of u_NS (row y-NS-1) and full weighting (coarse row when that row is odd) ----
-        if (MODE == MODE_PRE) {
+        if (C::HAS_PRE) {
             const int rr = y - NS - 1;
             T ff[V], o[V];
             ldv<T>(rslot<PH, NS + 1>() + 32 * V, ff);
@@ -344,7 +352,7 @@ struct Streamer {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             blk[j] = ring + ((q + j) & 3) * BLK;
-            if (MODE == MODE_POST) cblk[j] = cring + ((q + j) & 3) * CBLK;
+            if (C::HAS_POST) cblk[j] = cring + ((q + j) & 3) * CBLK;
         }
     }
 
@@ -391,7 +399,7 @@ struct Streamer {
         safe_f = a.f + (i64)a.row_lo * a.pitch;
         safe_c = a.ec;
         g_c = a.ec;
-        if (MODE == MODE_POST) {
+        if (C::HAS_POST) {
             safe_c = a.ec + (i64)a.crow_lo * a.pitch_c;
             g_c = a.ec + (i64)((ylo + 1) >> 1) * a.pitch_c + (c >> 1);
         }

@@ -206,6 +206,10 @@ class Multigrid:
     def cycle(self, level: Optional[int] = None, nu1: int = 2, nu2: int = 2, gamma: int = 1):
         self._ck(self._lib.mg_cycle(self._ctx, level or self.finest_level, nu1, nu2, gamma))
 
+    def cycles(self, count: int, level: Optional[int] = None, nu1: int = 2, nu2: int = 2, gamma: int = 1):
+        """`count` consecutive cycles (the loop P:646-648); same bits as `count` calls of cycle()."""
+        self._ck(self._lib.mg_cycles(self._ctx, level or self.finest_level, nu1, nu2, gamma, count))
+
     def fmg(self, cycles_per_level: int = 1, nu1: int = 2, nu2: int = 2):
         self._ck(self._lib.mg_fmg(self._ctx, cycles_per_level, nu1, nu2))
 

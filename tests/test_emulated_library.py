@@ -57,9 +57,10 @@ def test_gpu_parity_suite_under_emulation():
 
 
 def test_optin_paths_under_emulation():
-    """Tile kernels, zero-guess chain and the cluster coarse tail (16- and 4-CTA clusters) through the real host code."""
+    """Tile kernels, zero-guess chain, POST+PRE visit chains and the cluster coarse tail (16- and 4-CTA clusters) through
+    the real host code."""
     out = child_pytest(["tests/test_optin_gpu.py", "-k",
-                        "(tile_kernels_cycles or zero_guess or cluster_tail) and not [10- and not [8- and not -8-float and not -1-float"],
+                        "(tile_kernels_cycles or zero_guess or cluster_tail or visit_chain) and not [10- and not [8- and not -8-float and not -1-float"],
                        {"MGB200_TEST_OPTIN": "1"})
     assert " passed" in out and "failed" not in out
 

@@ -105,6 +105,50 @@ def test_cluster_tail_cycles_bitwise(mgb, orc, knob, level, ctas, dtype):
                     assert_bitwise(mg.get_u(level), want[k + 1], f"ctail cycle {k + 1} C={ctas} graph={graph} {smoother} g={gamma}")
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("smoother,nu1,nu2", [("jacobi", 2, 2), ("jacobi", 1, 1), ("jacobi", 1, 2), ("jacobi", 2, 1), ("jacobi", 3, 1),
+                                              ("rbgs", 1, 1), ("rbgs", 2, 2)])
+@pytest.mark.parametrize("level", [3, 5, 7, 8, 10])
+def test_visit_chain_postpre_bitwise(mgb, orc, knob, level, dtype, smoother, nu1, nu2):
+    """MGB200_CHAIN=1: POST of one visit of a level and PRE of the next visit are one POSTPRE launch -- consecutive cycles
+    through mg_cycles (the loop P:646-648) and the gamma visits of a W-cycle through mg_cycle; fullmultigrid uses it per
+    level.  Same bits as the same number of separate cycles."""
+    knob("MGB200_CHAIN", "1")
+    x, b = rand_vec(level, dtype, 87), rand_vec(level, dtype, 88, 1e-3)
+    sid = 1 if smoother == "rbgs" else 0
+    for gamma, count in ((1, 3), (2, 1), (2, 2)):
+        p = oracle.Params(nu1=nu1, nu2=nu2, gamma=gamma, smoother=sid, nthreads=4)
+        want = [x]
+        for _ in range(2 * count):
+            want.append(orc.vcyclemultigrid(want[-1], b, p))
+        for graph, tail in ((False, False), (True, True)):
+            with mgb.Multigrid(level, dtype=dtype, smoother=smoother, graph=graph, coarse_tail=tail) as mg:
+                mg.set_u(level, x)
+                mg.set_rhs(level, b)
+                mg.cycles(count, level, nu1, nu2, gamma)
+                assert_bitwise(mg.get_u(level), want[count], f"chain g={gamma} n={count} graph={graph} tail={tail}")
+                mg.cycles(count, level, nu1, nu2, gamma)      # replay from the new buffer parities
+                assert_bitwise(mg.get_u(level), want[2 * count], f"chain replay g={gamma} n={count} graph={graph}")
+    pv = oracle.Params(nu1=nu1, nu2=nu2, smoother=sid, nthreads=4)
+    with mgb.Multigrid(level, dtype=dtype, smoother=smoother) as mg:
+        assert_bitwise(mg.fullmultigrid(b, 3, nu1, nu2), orc.fullmultigrid(b, 3, pv), "fmg, 3 chained cycles per level")
+
+
+def test_visit_chain_really_fuses(mgb, knob):
+    """Launch counts: 3 chained V(2,2) cycles at 513^2 save two launches on the finest level, a W-cycle one per level."""
+    counts = {}
+    for chain in ("0", "1"):
+        knob("MGB200_CHAIN", chain)
+        for gamma, n in ((1, 3), (2, 1)):
+            with mgb.Multigrid(9, graph=False) as mg:
+                mg.force_constant(4.0)
+                mg.zero_u(9)
+                l0 = mg.launches
+                mg.cycles(n, 9, 2, 2, gamma)
+                counts[chain, gamma] = mg.launches - l0
+    assert counts["1", 1] == counts["0", 1] - 2 and counts["1", 2] < counts["0", 2]
+
+
 def test_tile_kernels_full_size_and_speed(mgb, orc, knob):
     """4097^2: the tile kernels take over levels <= 10; result must not change, cycle must not get slower."""
     level = 12

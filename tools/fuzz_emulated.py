@@ -33,7 +33,7 @@ def main():
         nu1, nu2 = int(rng.integers(0, 5)), int(rng.integers(0, 5))
         gamma = int(rng.integers(1, 4))
         flags = dict(graph=bool(rng.integers(0, 2)), fused=bool(rng.integers(0, 2)), coarse_tail=bool(rng.integers(0, 2)))
-        env = {k: str(int(rng.integers(0, 2))) for k in ("MGB200_TILE", "MGB200_ZERO_GUESS", "MGB200_CTAIL")}
+        env = {k: str(int(rng.integers(0, 2))) for k in ("MGB200_TILE", "MGB200_ZERO_GUESS", "MGB200_CTAIL", "MGB200_CHAIN")}
         env["MGB200_CTAIL_CTAS"] = str([1, 2, 4, 8, 16][int(rng.integers(0, 5))])
         if os.environ.get("FUZZ_DEFAULT_ONLY") == "1":
             env = {k: "0" for k in env}
@@ -50,10 +50,15 @@ def main():
                 mg.set_rhs(level, b)
                 want = x
                 for k in range(int(rng.integers(1, 4))):
-                    mg.cycle(level, nu1, nu2, gamma)
-                    want = o.vcyclemultigrid(want, b, p)
+                    cnt = int(rng.integers(1, 4))                  # 1: mg_cycle, > 1: mg_cycles (visit chains)
+                    if cnt == 1:
+                        mg.cycle(level, nu1, nu2, gamma)
+                    else:
+                        mg.cycles(cnt, level, nu1, nu2, gamma)
+                    for _ in range(cnt):
+                        want = o.vcyclemultigrid(want, b, p)
                     if not np.array_equal(mg.get_u(level), want):
-                        raise AssertionError(f"cycle {k + 1} differs, max {np.abs(mg.get_u(level) - want).max():.3e}")
+                        raise AssertionError(f"cycle {k + 1} (x{cnt}) differs, max {np.abs(mg.get_u(level) - want).max():.3e}")
                 # an operator sequence after the cycles, then another cycle (state bookkeeping across API calls)
                 nrm = mg.residual(level, norm=True)
                 r = o.residual(want, b)

@@ -13,7 +13,7 @@ timeout 600 python -m pytest tests -m gpu -x -q > $O/r02_pytest_default.log 2>&1
 tail -3 $O/r02_pytest_default.log
 
 step "opt-in paths (tile kernels, zero-guess chain, cluster tail)"
-MGB200_TEST_OPTIN=1 timeout 600 python -m pytest tests/test_optin_gpu.py -m gpu -q -k "tile_kernels_cycles or zero_guess or cluster_tail" \
+MGB200_TEST_OPTIN=1 timeout 600 python -m pytest tests/test_optin_gpu.py -m gpu -q -k "tile_kernels_cycles or zero_guess or cluster_tail or visit_chain" \
     > $O/r02_pytest_optin.log 2>&1; echo "rc=$?" >> $O/r02_pytest_optin.log
 tail -3 $O/r02_pytest_optin.log
 
@@ -42,6 +42,9 @@ run_bench ctail8 MGB200_CTAIL=1 MGB200_CTAIL_CTAS=8
 run_bench zg_tile MGB200_ZERO_GUESS=1 MGB200_TILE=1
 run_bench zg_ctail16 MGB200_ZERO_GUESS=1 MGB200_CTAIL=1
 run_bench zg_tile_ctail16 MGB200_ZERO_GUESS=1 MGB200_TILE=1 MGB200_CTAIL=1
+run_bench chain MGB200_CHAIN=1
+run_bench chain_zg MGB200_CHAIN=1 MGB200_ZERO_GUESS=1
+run_bench chain_zg_tile_ctail16 MGB200_CHAIN=1 MGB200_ZERO_GUESS=1 MGB200_TILE=1 MGB200_CTAIL=1
 step "other BASELINE configs on one GPU"
 timeout 300 python bench.py --no-cpu --no-e2e --level 13 --gamma 2 > $O/r02_bench_cfg4_W_8193.json 2>> $O/r02_steps.log
 timeout 300 python bench.py --no-cpu --no-e2e --level 14 --smoother rbgs > $O/r02_bench_cfg3_rbgs_16385_n1.json 2>> $O/r02_steps.log
