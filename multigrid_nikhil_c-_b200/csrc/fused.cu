@@ -153,7 +153,11 @@ static void raw_launch(Ctx& ctx, const StreamArgs<T>& a)
     const unsigned grid = cdiv(a.nitems, kStreamWarps);
     // cap the resident warps per SM at g_occ by padding the dynamic shared memory
     const size_t smem = std::min<size_t>(100 * 1024, std::max<size_t>(C::SMEM_BYTES, (size_t)(227 * 1024) / std::max(1, g_occ / kStreamWarps) - 1024));
-    k_stream<T, NS, MODE, RBGS><<<grid, kStreamWarps * 32, smem, ctx.stream>>>(a);
+    if constexpr (MODE == MODE_POSTPRE) {
+        k_stream_chain<T, NS, RBGS><<<grid, kStreamWarps * 32, smem, ctx.stream>>>(a);
+    } else {
+        k_stream<T, NS, MODE, RBGS><<<grid, kStreamWarps * 32, smem, ctx.stream>>>(a);
+    }
     ++ctx.lc.n;
     MG_CK(cudaGetLastError());
 }
@@ -502,7 +506,7 @@ static void launch_postpre(Ctx& ctx, Level& lv, Level& lcv, bool write_zero_gues
     typedef StreamCfg<T, NS, MODE_POSTPRE> C;
     static bool attr_set = false;
     if (!attr_set) {
-        MG_CK(cudaFuncSetAttribute(k_stream<T, NS, MODE_POSTPRE, RBGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MG_CK(cudaFuncSetAttribute(k_stream_chain<T, NS, RBGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)std::max<size_t>(C::SMEM_BYTES, 100 * 1024)));
         attr_set = true;
     }

@@ -445,6 +445,20 @@ k_stream(const StreamArgs<T> a)
     st.run(reinterpret_cast<T*>(stream_smem), warp, threadIdx.x & 31, item);
 }
 
+// POSTPRE (visit chains, opt-in MGB200_CHAIN=1) needs ~142 registers at NS = 4: its own entry point with a launch bound
+// of 12 resident CTAs per SM (the occupancy the host caps the streaming kernels at anyway) instead of 16 => no spills
+constexpr int kStreamChainMinCtas = 12;
+template <typename T, int NS, bool RBGS>
+__global__ void __launch_bounds__(kStreamWarps * 32, kStreamChainMinCtas / kStreamWarps)
+k_stream_chain(const StreamArgs<T> a)
+{
+    extern __shared__ __align__(16) unsigned char stream_smem[];
+    const int warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * kStreamWarps + warp;
+    Streamer<T, NS, MODE_POSTPRE, RBGS> st(a);
+    st.run(reinterpret_cast<T*>(stream_smem), warp, threadIdx.x & 31, item);
+}
+
 // zero-guess variant of the PRE kernel (opt-in, MGB200_ZERO_GUESS=1): a separate kernel so that k_stream itself
 // stays byte-identical to the GPU-verified build
 template <typename T, int NS, bool RBGS>
