@@ -178,6 +178,11 @@ void Ctx::sync() { MG_CK(cudaStreamSynchronize(stream)); }
 // write the zeros of a logically-zero iterate (no-op unless MGB200_ZERO_GUESS left one pending)
 void Ctx::materialize_u(Level& lv)
 {
+    if (lv.u_interp) {           // pending bare interpolation (fullmultigrid entry, MGB200_CHAIN)
+        lv.u_interp = false;
+        prolong(lv.level, false);
+        return;
+    }
     if (!lv.u_zero) return;
     MG_CK(cudaMemsetAsync(lv.alloc[lv.cur], 0, lv.bytes, stream));
     lv.u_zero = false;
@@ -205,7 +210,7 @@ std::string Ctx::state_blob() const
     std::string b;
     for (int l = cfg.coarsest_level; l <= cfg.finest_level; ++l) {
         const Level& lv = levels[l];
-        b.push_back((char)(lv.cur | (lv.u_zero ? 2 : 0)));
+        b.push_back((char)(lv.cur | (lv.u_zero ? 2 : 0) | (lv.u_interp ? 4 : 0)));
         if (lv.distributed) {
             b.push_back((char)lv.hv_u);
             b.push_back((char)lv.hv_f);
@@ -222,6 +227,7 @@ void Ctx::set_state(const std::string& blob)
         Level& lv = levels[l];
         lv.cur = blob[k] & 1;
         lv.u_zero = (blob[k] & 2) != 0;
+        lv.u_interp = (blob[k] & 4) != 0;
         ++k;
         if (lv.distributed) {
             lv.hv_u = blob[k++];
@@ -249,7 +255,7 @@ void Ctx::set_host(int level, Which w, const void* host)
 {
     MG_REQUIRE(host != nullptr, "null host pointer");
     Level& lv = L(level);
-    if (w == W_U) lv.u_zero = false;   // overwritten below (ring rows / columns of every buffer are zero already)
+    if (w == W_U) lv.u_zero = lv.u_interp = false;   // overwritten below (ring rows / columns of every buffer are zero already)
     const i64 n = lv.N - 1;
     const int ya = std::max(lv.st_lo, 1), yb = std::min(lv.st_hi, lv.N);
     char* dst = which_ptr(lv, w) + ((i64)ya * lv.pitch + 1) * esize;
@@ -279,7 +285,7 @@ void Ctx::zero_u(int level)
     Level& lv = L(level);
     MG_CK(cudaMemsetAsync(lv.alloc[lv.cur], 0, lv.bytes, stream));
     lv.hv_u = lv.halo;
-    lv.u_zero = false;
+    lv.u_zero = lv.u_interp = false;
 }
 
 void Ctx::force_constant(double fval)
@@ -394,7 +400,8 @@ void Ctx::prolong_t(int fine_level, bool add)
     Level& lf = L(fine_level);
     Level& lcv = L(fine_level - 1);
     materialize_u(lcv);
-    materialize_u(lf);
+    if (add) materialize_u(lf);
+    else lf.u_zero = lf.u_interp = false;   // overwritten: whatever was pending is moot
     // the last owned fine row (odd) interpolates from the first coarse halo row
     ensure_halo(lcv, W_U, 1);
     launch_prolong<T>(stream, lc, (const T*)lcv.u[lcv.cur], lcv.pitch, (T*)lf.u[lf.cur], lf.pitch, lf.N, lf.own_lo,
@@ -503,7 +510,10 @@ void Ctx::fmg(int cycles, int nu1, int nu2)
     zero_u(cfg.coarsest_level);                                                          // P:630
     this->cycles(cfg.coarsest_level, nu1, nu2, 1, cycles);                               // P:635-637
     for (int l = cfg.coarsest_level + 1; l <= cfg.finest_level; ++l) {
-        prolong(l, false);                                                               // P:645
+        // P:645.  With visit chains on a single-GPU level the interpolation is left pending: the first PRE of the
+        // level interpolates on the fly (fused.cu: k_stream_fmg_entry); any other reader materialises it
+        if (chain && !L(l).distributed && !capturing) { materialize_u(L(l - 1)); L(l).u_zero = false; L(l).u_interp = true; }
+        else prolong(l, false);
         this->cycles(l, nu1, nu2, 1, cycles);                                            // P:646-648
     }
 }

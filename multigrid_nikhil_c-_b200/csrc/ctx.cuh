@@ -62,6 +62,10 @@ struct Level {
     // MGB200_ZERO_GUESS: the current u is LOGICALLY zero but its buffer was not written (the next kernel is a
     // zero-guess variant that does not read it); Ctx::materialize_u writes the zeros for every other reader
     bool u_zero = false;
+    // MGB200_CHAIN, fullmultigrid: the current u is LOGICALLY the bare interpolation of the coarser level's iterate
+    // (P:645) but was not computed: the first PRE of the level does it on the fly (k_stream_fmg_entry);
+    // Ctx::materialize_u runs the real prolongation for every other reader
+    bool u_interp = false;
 };
 
 struct GraphEntry {

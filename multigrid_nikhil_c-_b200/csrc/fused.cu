@@ -394,11 +394,17 @@ static void stream_sweeps(Ctx& ctx, Level& lv, int nu)
     }
 }
 
+template <typename T> static bool fmg_entry_fused(Ctx& ctx, Level& lv, Level& lcv, int nu1);
+
 template <typename T>
 static void pre_fused(Ctx& ctx, Level& lv, Level& lcv, int nu1)
 {
     const int k = std::min(nu1, 2);
     const bool rb = ctx.cfg.smoother == MG_SMOOTH_RBGS;
+    if (lv.u_interp) {   // fullmultigrid entry (MGB200_CHAIN): interpolate the coarse solution inside this PRE
+        if (fmg_entry_fused<T>(ctx, lv, lcv, nu1)) return;
+        ctx.materialize_u(lv);
+    }
     if (ctx.zero_guess && !use_tile(lv) && !lv.distributed) {
         // opt-in zero-guess chain
         const bool wz = !child_takes_zero_guess(ctx, lv, nu1);
@@ -494,7 +500,7 @@ static void post_fused(Ctx& ctx, Level& lv, Level& lcv, int nu2)
 // ---------------------------------------------------------------------------------
 static int postpre_ns(const Ctx& ctx, const Level& lv, int nu1, int nu2)
 {
-    if (!ctx.chain || !(ctx.cfg.flags & MG_FUSED) || lv.distributed || use_tile(lv)) return 0;
+    if (!ctx.chain || !(ctx.cfg.flags & MG_FUSED) || use_tile(lv) || (lv.distributed && ctx.comm_avoid)) return 0;
     if (nu1 < 1 || nu2 < 1 || nu1 > 2 || nu2 > 2) return 0;
     if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) return nu1 + nu2;          // 2, 3 or 4 pipeline stages
     return (nu1 == 1 && nu2 == 1) ? 4 : 0;                               // RB-GS: one stage per colour
@@ -512,8 +518,13 @@ static void launch_postpre(Ctx& ctx, Level& lv, Level& lcv, bool write_zero_gues
     }
     ctx.materialize_u(lv);
     ctx.materialize_u(lcv);
+    // row slabs: halo rows the pipeline reaches into (PRE's needs on u and f, POST's on the coarse correction)
+    ctx.ensure_halo(lv, Ctx::W_U, NS + 2);
+    ctx.ensure_halo(lv, Ctx::W_F, NS + 1);
+    ctx.ensure_halo(lcv, Ctx::W_U, (NS + 2) / 2 + 1);
+    const bool gather = lv.distributed && !lcv.distributed;   // agglomeration boundary: zero guess by memset after the all-gather
     const int ry = tuned_ry<T, NS, MODE_POSTPRE, RBGS>(ctx, lv, &lcv);
-    const StreamArgs<T> a = make_args<T, NS, MODE_POSTPRE>(ctx, lv, &lcv, ry, -1, -1, write_zero_guess);
+    const StreamArgs<T> a = make_args<T, NS, MODE_POSTPRE>(ctx, lv, &lcv, ry, -1, -1, write_zero_guess && !gather);
     raw_launch<T, NS, MODE_POSTPRE, RBGS>(ctx, a);
     lv.cur ^= 1;
     lv.hv_u = 0;
@@ -522,6 +533,16 @@ static void launch_postpre(Ctx& ctx, Level& lv, Level& lcv, bool write_zero_gues
         lcv.u_zero = false;
     } else {
         lcv.u_zero = true;       // zero-guess chain: the child's first kernel does not read its iterate
+    }
+    if (gather) {
+        comm_allgather_rows(ctx, lcv, lcv.f);
+        if (write_zero_guess) MG_CK(cudaMemsetAsync(lcv.alloc[lcv.cur], 0, lcv.bytes, ctx.stream));
+    } else if (lcv.distributed) {
+        lcv.hv_f = 0;
+        if (write_zero_guess) {
+            comm_zero_halo(ctx, lcv, lcv.u[lcv.cur]);
+            lcv.hv_u = lcv.halo;
+        }
     }
 }
 
@@ -536,6 +557,50 @@ static void postpre_fused(Ctx& ctx, Level& lv, Level& lcv, int ns, int nu1)
     } else {
         launch_postpre<T, 4, true>(ctx, lv, lcv, wz);
     }
+}
+
+// fullmultigrid's entry into a level: interpolation of the coarse solution (P:645) + PRE of the first cycle in one launch
+template <typename T, int NS, bool RBGS>
+static void launch_fmg_entry(Ctx& ctx, Level& lv, Level& lcv, bool write_zero_guess)
+{
+    typedef StreamCfg<T, NS, MODE_POSTPRE> C;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MG_CK(cudaFuncSetAttribute(k_stream_fmg_entry<T, NS, RBGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    ctx.materialize_u(lcv);
+    lv.u_interp = false;                       // consumed here: stage 0 of the kernel is P u_c
+    StreamArgs<T> a = make_args<T, NS, MODE_POSTPRE>(ctx, lv, &lcv, 0, -1, -1, write_zero_guess);
+    if (a.yb > a.ya) {
+        const size_t smem = std::min<size_t>(100 * 1024, std::max<size_t>(C::SMEM_BYTES, (size_t)(227 * 1024) / std::max(1, g_occ / kStreamWarps) - 1024));
+        k_stream_fmg_entry<T, NS, RBGS><<<cdiv(a.nitems, kStreamWarps), kStreamWarps * 32, smem, ctx.stream>>>(a);
+        ++ctx.lc.n;
+        MG_CK(cudaGetLastError());
+    }
+    lv.cur ^= 1;
+    lv.hv_u = 0;
+    if (write_zero_guess) {
+        lcv.cur ^= 1;
+        lcv.u_zero = false;
+    } else {
+        lcv.u_zero = true;
+    }
+}
+
+template <typename T>
+static bool fmg_entry_fused(Ctx& ctx, Level& lv, Level& lcv, int nu1)
+{
+    if (!ctx.chain || lv.distributed || use_tile(lv) || nu1 < 1 || nu1 > 2) return false;
+    const bool wz = !child_takes_zero_guess(ctx, lv, nu1);
+    if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) {
+        if (nu1 == 2) launch_fmg_entry<T, 2, false>(ctx, lv, lcv, wz);
+        else launch_fmg_entry<T, 1, false>(ctx, lv, lcv, wz);
+    } else {
+        if (nu1 == 2) launch_fmg_entry<T, 4, true>(ctx, lv, lcv, wz);
+        else launch_fmg_entry<T, 2, true>(ctx, lv, lcv, wz);
+    }
+    return true;
 }
 
 // ---------------------------------------------------------------------------------
@@ -554,6 +619,7 @@ template <typename T>
 static void run_tail(Ctx& ctx, int level, int nu1, int nu2, int gamma)
 {
     Level& lv = ctx.L(level);
+    if (lv.u_interp) ctx.materialize_u(lv);
     TailArgs<T> a;
     a.top = level;
     a.coarsest = ctx.cfg.coarsest_level;

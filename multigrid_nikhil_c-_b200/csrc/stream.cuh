@@ -254,7 +254,7 @@ struct Streamer {
                 }
             }
 #pragma unroll
-            for (int k = 0; k < V; ++k) cur[k] = ring_row(y) ? (T)0 : cur[k] + e[k];           // P:623
+            for (int k = 0; k < V; ++k) cur[k] = ring_row(y) ? (T)0 : (ZG ? e[k] : cur[k] + e[k]);   // P:623 (ZG: bare interpolation, P:645)
             mask_cols(cur);
         }
         put_row<NEW>(0, cur);
@@ -456,6 +456,19 @@ k_stream_chain(const StreamArgs<T> a)
     const int warp = threadIdx.x >> 5;
     const int item = blockIdx.x * kStreamWarps + warp;
     Streamer<T, NS, MODE_POSTPRE, RBGS> st(a);
+    st.run(reinterpret_cast<T*>(stream_smem), warp, threadIdx.x & 31, item);
+}
+
+// fullmultigrid's entry into a level (P:645-646): the bare interpolation of the coarse solution as initial guess fused with
+// the first cycle's PRE -- POSTPRE with "the incoming iterate is zero and is not read", stage 0 = P u_c
+template <typename T, int NS, bool RBGS>
+__global__ void __launch_bounds__(kStreamWarps * 32, kStreamChainMinCtas / kStreamWarps)
+k_stream_fmg_entry(const StreamArgs<T> a)
+{
+    extern __shared__ __align__(16) unsigned char stream_smem[];
+    const int warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * kStreamWarps + warp;
+    Streamer<T, NS, MODE_POSTPRE, RBGS, true> st(a);
     st.run(reinterpret_cast<T*>(stream_smem), warp, threadIdx.x & 31, item);
 }
 

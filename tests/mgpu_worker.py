@@ -83,8 +83,19 @@ def main():
                         want = o.vcyclemultigrid(want, b, p)
                         check(mg, level, mg.get_u(level), want, f"cycle {k} gamma={gamma} {smoother} L{level} aggl{aggl}")
                         n_checks += 1
+                # consecutive cycles in one call (mg_cycles; with MGB200_CHAIN=1 POST+PRE visit chains on the slabs)
+                for nu, cnt in ((2, 3), (1, 2)):
+                    p = oracle.Params(nu1=nu, nu2=nu, smoother=sid, nthreads=2)
+                    mg.set_u(level, x); mg.set_rhs(level, b)
+                    mg.cycles(cnt, level, nu, nu, 1)
+                    want = x
+                    for _ in range(cnt):
+                        want = o.vcyclemultigrid(want, b, p)
+                    check(mg, level, mg.get_u(level), want, f"{cnt} chained V({nu},{nu}) {smoother} L{level} aggl{aggl}")
+                    n_checks += 1
                 p = oracle.Params(smoother=sid, nthreads=2)
                 check(mg, level, mg.fullmultigrid(b, 1, 2, 2), o.fullmultigrid(b, 1, p), "fmg")
+                check(mg, level, mg.fullmultigrid(b, 2, 1, 1), o.fullmultigrid(b, 2, oracle.Params(nu1=1, nu2=1, smoother=sid, nthreads=2)), "fmg 2x V(1,1)")
                 mg.set_rhs(level, b); mg.zero_u(level)
                 k, rel, hist = mg.solve(1e-8, 30)
                 u, ko, ho = o.solve(np.zeros_like(b), b, 1e-8, 30, p)

@@ -129,9 +129,18 @@ def test_visit_chain_postpre_bitwise(mgb, orc, knob, level, dtype, smoother, nu1
                 assert_bitwise(mg.get_u(level), want[count], f"chain g={gamma} n={count} graph={graph} tail={tail}")
                 mg.cycles(count, level, nu1, nu2, gamma)      # replay from the new buffer parities
                 assert_bitwise(mg.get_u(level), want[2 * count], f"chain replay g={gamma} n={count} graph={graph}")
+    # fullmultigrid: the interpolation of the coarse solution (P:645) is fused into the first PRE of each level
+    # (k_stream_fmg_entry), its cycles per level are chained
     pv = oracle.Params(nu1=nu1, nu2=nu2, smoother=sid, nthreads=4)
-    with mgb.Multigrid(level, dtype=dtype, smoother=smoother) as mg:
-        assert_bitwise(mg.fullmultigrid(b, 3, nu1, nu2), orc.fullmultigrid(b, 3, pv), "fmg, 3 chained cycles per level")
+    for graph, tail in ((False, False), (True, True)):
+        with mgb.Multigrid(level, dtype=dtype, smoother=smoother, graph=graph, coarse_tail=tail) as mg:
+            for cyc in (1, 3):
+                assert_bitwise(mg.fullmultigrid(b, cyc, nu1, nu2), orc.fullmultigrid(b, cyc, pv), f"fmg, {cyc} cycles per level")
+            # a pending interpolation must be materialised for any other reader
+            if level > 2:
+                mg.set_rhs(level, b)
+                mg.fmg(1, nu1, nu2)
+                assert_bitwise(mg.get_u(level), orc.fullmultigrid(b, 1, pv), "resident fmg")
 
 
 def test_visit_chain_really_fuses(mgb, knob):
