@@ -61,14 +61,16 @@ void fused_setup(Ctx& ctx)
     cudaDeviceProp prop;
     MG_CK(cudaGetDeviceProperties(&prop, ctx.device));
     g_num_sms = prop.multiProcessorCount;
-    if (const char* e = getenv("MGB200_STREAM_RY")) g_force_ry = atoi(e);
-    if (const char* e = getenv("MGB200_STREAM_RY_MINN")) g_force_ry_minN = atoi(e);
-    if (const char* e = getenv("MGB200_STREAM_OCC")) g_occ = std::max(1, atoi(e));
-    if (const char* e = getenv("MGB200_AUTOTUNE")) g_autotune = atoi(e) != 0;
-    if (const char* e = getenv("MGB200_TILE")) g_tile = atoi(e) != 0;
-    if (const char* e = getenv("MGB200_CTAIL")) g_ctail = atoi(e) != 0;
-    if (const char* e = getenv("MGB200_CTAIL_CTAS")) g_ctail_ctas = std::max(1, std::min(kCtailMaxCtas, atoi(e)));
-    if (const char* e = getenv("MGB200_TILE_MAXN")) g_tile_maxN = atoi(e);
+    // run-time knobs: read afresh for every context (absent variable = default, so a knob never sticks in a process)
+    auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    g_force_ry = env_int("MGB200_STREAM_RY", 0);
+    g_force_ry_minN = env_int("MGB200_STREAM_RY_MINN", 4096);
+    g_occ = std::max(1, env_int("MGB200_STREAM_OCC", 12));
+    g_autotune = env_int("MGB200_AUTOTUNE", 1) != 0;
+    g_tile = env_int("MGB200_TILE", 0) != 0;
+    g_tile_maxN = env_int("MGB200_TILE_MAXN", 1024);
+    g_ctail = env_int("MGB200_CTAIL", 0) != 0;
+    g_ctail_ctas = std::max(1, std::min(kCtailMaxCtas, env_int("MGB200_CTAIL_CTAS", 16)));
     if (ctx.f64()) set_attrs_t<double>();
     else set_attrs_t<float>();
 }
