@@ -67,6 +67,12 @@ class StubMG:
     def fullmultigrid(self, f, cycles, nu1, nu2, out=None):
         return out if out is not None else np.zeros_like(f)
 
+    def fmg(self, cycles, nu1, nu2):
+        pass
+
+    def sync(self):
+        pass
+
     def vcyclemultigrid_slab(self, level, u, f, nu1, nu2, gamma):
         assert u.size == f.size
 
