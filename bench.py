@@ -116,6 +116,40 @@ def synthetic_rhs(level: int, dtype) -> np.ndarray:
     return (h * h * np.random.default_rng(1234).uniform(-1.0, 1.0, n * n)).astype(dtype)
 
 
+class GpuLocalAffinity:
+    """Bind the calling thread to the CPUs that are local to a GPU (NVML's CPU affinity) while the pinned host buffers
+    are allocated and first touched, so that they live on the GPU's NUMA node; the previous affinity is restored on
+    exit (the CPU baseline and OpenMP must see all cores).  Best effort: any failure leaves everything as it was."""
+
+    def __init__(self, device: int):
+        self.device, self.saved, self.cpus = device, None, None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+            allowed = os.sched_getaffinity(0)
+            cpus &= allowed
+            if cpus and cpus != allowed:
+                self.saved = allowed
+                os.sched_setaffinity(0, cpus)
+                self.cpus = len(cpus)
+        except Exception:
+            self.saved = None
+        return self
+
+    def __exit__(self, *a):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:
+                pass
+
+
 def pinned(nelem: int, dtype):
     import torch
     t = torch.empty(nelem, dtype={np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}[np.dtype(dtype)],
@@ -229,6 +263,8 @@ def run_ours(args, rank, world, local_rank):
                           comm_id=comm, graph=not args.no_graph, fused=not args.no_fused,
                           coarse_tail=not args.no_tail, agglomerate_level=args.aggl)
     slab = world > 1 and not args.full_host_vectors
+    numa = GpuLocalAffinity(local_rank)
+    numa.__enter__()           # host buffers below are allocated and first touched on the GPU's NUMA node
     if slab:
         # a rank only ever touches the interior rows it stores: keep just those on the host (Multigrid.set_rhs_slab)
         ya, yb = mg.slab_rows(level)
@@ -245,6 +281,7 @@ def run_ours(args, rank, world, local_rank):
         f_host[:] = synthetic_rhs(level, dtype)
         u_host[:] = 0
         mg.set_rhs(level, f_host)
+    numa.__exit__()
     mg.zero_u(level)
     upd = updates_per_cycle(level, 1, nu1, nu2, gamma)
 
@@ -349,7 +386,8 @@ def run_ours(args, rank, world, local_rank):
     e2e = {"value": upd / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
            "h2d_bytes_per_step": 2 * (n if world == 1 else mg.slab_rows(level)[1] - mg.slab_rows(level)[0]) * n * esize,
            "d2h_bytes_per_step": rows * n * esize,
-           "call": "mg_host_vcyclemultigrid (vcyclemultigrid P:575 on pinned host vectors)"}
+           "call": "mg_host_vcyclemultigrid (vcyclemultigrid P:575 on pinned host vectors)",
+           "host_buffers_on_gpu_numa_node_cpus": numa.cpus}
 
     # informational: the reference's top-level call shape, fullmultigrid(f_h) -> u (P:629 / main P:727): one H2D of f,
     # one V(2,2) per level on the way up, one D2H of u.  Transfers are amortised over ~4/3 cycles' worth of work.
