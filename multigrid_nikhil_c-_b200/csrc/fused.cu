@@ -169,6 +169,7 @@ static void raw_launch(Ctx& ctx, const StreamArgs<T>& a)
 // so it is picked once by timing a few candidates.  Tuning launches write only scratch state (the non-current
 // u buffer and, for PRE, the coarse f / zero guess that the real launch rewrites), results never depend on it.
 constexpr int kTuneMinN = 2048;
+constexpr int kTuneReps = 4;   // timed launches per candidate (after one warm-up)
 
 template <typename T, int NS, int MODE, bool RBGS>
 static int tuned_ry(Ctx& ctx, Level& lv, Level* lcv)
@@ -198,10 +199,9 @@ static int tuned_ry(Ctx& ctx, Level& lv, Level* lcv)
     int best_ry = a0.ry;
     for (int ry : cand) {
         StreamArgs<T> a = make_args<T, NS, MODE>(ctx, lv, lcv, ry);
-        raw_launch<T, NS, MODE, RBGS>(ctx, a);
+        raw_launch<T, NS, MODE, RBGS>(ctx, a);   // warm-up
         MG_CK(cudaEventRecord(e0, ctx.stream));
-        raw_launch<T, NS, MODE, RBGS>(ctx, a);
-        raw_launch<T, NS, MODE, RBGS>(ctx, a);
+        for (int rep = 0; rep < kTuneReps; ++rep) raw_launch<T, NS, MODE, RBGS>(ctx, a);
         MG_CK(cudaEventRecord(e1, ctx.stream));
         MG_CK(cudaEventSynchronize(e1));
         float ms = 0.f;
@@ -210,7 +210,7 @@ static int tuned_ry(Ctx& ctx, Level& lv, Level* lcv)
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    ctx.lc.n -= 3 * (long long)cand.size();   // tuning launches are not part of the work
+    ctx.lc.n -= (1 + kTuneReps) * (long long)cand.size();   // tuning launches are not part of the work
     ctx.stream_ry[key] = best_ry;
     return best_ry;
 }
