@@ -443,6 +443,7 @@ def run_ours(args, rank, world, local_rank):
                        "l2_policy": "inputs larger than L2 (4 arrays x %.0f MB on the finest level)" % (n * n * esize / 1e6),
                        "regions": regions, "region_stat": "median", "agglomerate_level": mg.info(capi.MG_INFO_AGGLOMERATE_LEVEL, level) if world > 1 else None,
                        "timed_as": f"{K} consecutive cycles per region through mg_time_cycle (mg_cycles)",
+                       "env_knobs": {k: v for k, v in sorted(os.environ.items()) if k.startswith("MGB200_")},
                        "flags": {"visit_chain": os.environ.get("MGB200_CHAIN") == "1", "graph": not args.no_graph,
                                                                               "fused": not args.no_fused,
                                                                               "coarse_tail": not args.no_tail}},
