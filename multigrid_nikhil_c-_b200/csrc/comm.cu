@@ -132,21 +132,22 @@ void comm_destroy(Comm* c)
     delete c;
 }
 
-void comm_halo_exchange(Ctx& ctx, Level& lv, char* base, int depth)
+void comm_halo_exchange(Ctx& ctx, Level& lv, char* base, int depth, cudaStream_t stream)
 {
     Comm* c = ctx.comm;
     if (!c || !lv.distributed) return;
+    if (!stream) stream = ctx.stream;
     const size_t row_bytes = (size_t)lv.pitch * ctx.esize;
     const size_t bytes = row_bytes * depth;
     auto row = [&](int y) { return base + (size_t)y * row_bytes; };
     NC(nccl().GroupStart());
     if (c->rank > 0) {  // neighbour above (smaller row indices)
-        NC(nccl().Send(row(lv.own_lo), bytes, ncclChar, c->rank - 1, c->comm, ctx.stream));
-        NC(nccl().Recv(row(lv.own_lo - depth), bytes, ncclChar, c->rank - 1, c->comm, ctx.stream));
+        NC(nccl().Send(row(lv.own_lo), bytes, ncclChar, c->rank - 1, c->comm, stream));
+        NC(nccl().Recv(row(lv.own_lo - depth), bytes, ncclChar, c->rank - 1, c->comm, stream));
     }
     if (c->rank < c->world - 1) {  // neighbour below
-        NC(nccl().Send(row(lv.own_hi - depth), bytes, ncclChar, c->rank + 1, c->comm, ctx.stream));
-        NC(nccl().Recv(row(lv.own_hi), bytes, ncclChar, c->rank + 1, c->comm, ctx.stream));
+        NC(nccl().Send(row(lv.own_hi - depth), bytes, ncclChar, c->rank + 1, c->comm, stream));
+        NC(nccl().Recv(row(lv.own_hi), bytes, ncclChar, c->rank + 1, c->comm, stream));
     }
     NC(nccl().GroupEnd());
 }

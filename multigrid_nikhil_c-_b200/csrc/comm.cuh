@@ -11,7 +11,8 @@ void slab_rows(int level, int rank, int world, int* lo, int* hi);
 Comm* comm_create(Ctx& ctx);
 void comm_destroy(Comm* c);
 // exchange `depth` owned edge rows of the array at virtual base `base` with both neighbours
-void comm_halo_exchange(Ctx& ctx, Level& lv, char* base, int depth);
+// (on `stream`, default: the context's stream)
+void comm_halo_exchange(Ctx& ctx, Level& lv, char* base, int depth, cudaStream_t stream = nullptr);
 // clear the halo rows of `base`
 void comm_zero_halo(Ctx& ctx, Level& lv, char* base);
 // replicated level: every rank contributed its slab of rows of `base`; gather all slabs everywhere

@@ -136,6 +136,13 @@ Ctx::Ctx(const mg_config& c) : cfg(c)
         comm = comm_create(*this);
         const char* e = getenv("MGB200_GRAPH_DIST");
         graph_dist = e && e[0] == '1';
+        const char* ov = getenv("MGB200_OVERLAP");
+        overlap = ov && ov[0] == '1';
+        if (overlap) {
+            MG_CK(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+            MG_CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            MG_CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        }
     }
     {
         const char* zg = getenv("MGB200_ZERO_GUESS");
@@ -155,7 +162,11 @@ Ctx::~Ctx()
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (auto& kv : ctail_ops)
         if (kv.second.first) cudaFree(kv.second.first);
+    if (comm_stream) cudaStreamSynchronize(comm_stream);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     if (comm) comm_destroy(comm);
+    if (comm_stream) cudaStreamDestroy(comm_stream);
     for (auto& lv : levels)
         for (int k = 0; k < 4; ++k)
             if (lv.alloc[k]) cudaFree(lv.alloc[k]);

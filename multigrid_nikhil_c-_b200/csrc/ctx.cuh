@@ -97,6 +97,9 @@ struct Ctx {
     bool graph_dist = false;  // capture NCCL exchanges into cycle graphs (MGB200_GRAPH_DIST=1)
     bool zero_guess = false;  // skip reading / writing the zero coarse guess (MGB200_ZERO_GUESS=1)
     bool comm_avoid = false;  // communication-avoiding slab schedule (MGB200_COMM_AVOID=1, csrc/sched.h)
+    bool overlap = false;     // halo exchange on a second stream, overlapped with the interior rows (MGB200_OVERLAP=1)
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool chain = false;       // fuse POST of one visit of a level with PRE of the next (MGB200_CHAIN=1, stream.cuh MODE_POSTPRE)
 
     explicit Ctx(const mg_config& c);

@@ -66,6 +66,7 @@ enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cuda
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributeNonPortableClusterSizeAllowed = 12 };
 enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal = 0, cudaStreamCaptureModeThreadLocal = 1, cudaStreamCaptureModeRelaxed = 2 };
 enum { cudaStreamNonBlocking = 1 };
+enum { cudaEventDefault = 0, cudaEventBlockingSync = 1, cudaEventDisableTiming = 2 };
 enum cudaLaunchAttributeID { cudaLaunchAttributeClusterDimension = 4 };
 
 struct emuStream;
@@ -172,6 +173,8 @@ cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind 
 cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
                               cudaMemcpyKind k, cudaStream_t s);
 cudaError_t cudaEventCreate(cudaEvent_t* e);
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned flags);
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned flags = 0);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);

@@ -308,9 +308,19 @@ static void run_kernel(dim3 grid, dim3 block, size_t smem, unsigned cluster, con
 // ---------------------------------------------------------------------------------------------------------
 }  // namespace emu
 
-struct emuGraph { std::vector<std::function<void()>> ops; };
-struct emuStream { emuGraph* capture = nullptr; };
-struct emuEvent { std::chrono::steady_clock::time_point t; };
+struct emuGraph {
+    std::vector<std::function<void()>> ops;
+    int forked = 0;    // streams pulled into the capture and not joined back yet
+};
+struct emuStream {
+    emuGraph* capture = nullptr;
+    bool joined_capture = false;   // this stream was pulled into another stream's capture by cudaStreamWaitEvent (fork)
+};
+struct emuEvent {
+    std::chrono::steady_clock::time_point t;
+    emuStream* stream = nullptr;    // stream of the last record
+    emuGraph* capture = nullptr;    // the capture that record belonged to
+};
 
 namespace emu {
 
@@ -455,11 +465,31 @@ cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t 
 }
 
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emuEvent(); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new emuEvent(); return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s)
 {
-    if (s && s->capture) return cudaErrorStreamCaptureUnsupported;
     e->t = std::chrono::steady_clock::now();
+    e->stream = s;
+    e->capture = s ? s->capture : nullptr;   // inside a capture the record is a dependency edge, not a timestamp
+    return cudaSuccess;
+}
+// Streams execute synchronously, so outside a capture a wait has nothing to do.  Inside a capture it is the fork /
+// join of CUDA's cross-stream capture: waiting on an event recorded in a capturing stream pulls the waiting stream
+// into that capture; when the origin stream later waits on an event recorded in the pulled-in stream, that stream
+// leaves the capture again.  Work enqueued on a pulled-in stream is recorded into the same graph, in issue order.
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned)
+{
+    if (!s || !e) return cudaErrorInvalidValue;
+    if (e->capture && !s->capture) {          // fork
+        s->capture = e->capture;
+        s->joined_capture = true;
+        ++e->capture->forked;
+    } else if (e->capture && s->capture == e->capture && e->stream && e->stream != s && e->stream->joined_capture) {   // join
+        e->stream->capture = nullptr;
+        e->stream->joined_capture = false;
+        --e->capture->forked;
+    }
     return cudaSuccess;
 }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
@@ -477,7 +507,10 @@ cudaError_t cudaStreamBeginCapture(cudaStream_t s, cudaStreamCaptureMode)
 }
 cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t* g)
 {
-    if (!s || !s->capture) { *g = nullptr; return cudaErrorInvalidValue; }
+    if (!s || !s->capture || s->joined_capture || s->capture->forked != 0) {   // unjoined work in another stream
+        *g = nullptr;
+        return cudaErrorInvalidValue;
+    }
     *g = s->capture;
     s->capture = nullptr;
     return cudaSuccess;

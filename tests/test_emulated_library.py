@@ -50,7 +50,8 @@ def torchrun_cmd(world, script, *args):
 WORKER = os.path.join(ROOT, "tests", "mgpu_worker.py")
 BENCH_WORKER = os.path.join(ROOT, "tests", "host_emul", "bench_emu_worker.py")
 KNOBS = {"default": {}, "comm_avoid+graph_dist": {"MGB200_COMM_AVOID": "1", "MGB200_GRAPH_DIST": "1"},
-         "tile+zero_guess": {"MGB200_TILE": "1", "MGB200_ZERO_GUESS": "1"}, "chain+graph_dist": {"MGB200_CHAIN": "1", "MGB200_GRAPH_DIST": "1"}}
+         "tile+zero_guess": {"MGB200_TILE": "1", "MGB200_ZERO_GUESS": "1"}, "chain+graph_dist": {"MGB200_CHAIN": "1", "MGB200_GRAPH_DIST": "1"},
+         "overlap+graph_dist": {"MGB200_OVERLAP": "1", "MGB200_GRAPH_DIST": "1"}}
 BENCH = {"1rank": (1, []), "2ranks_slab_host_buffers": (2, ["--aggl", "5", "--level", "8"]), "rbgs_wcycle": (1, ["--smoother", "rbgs", "--gamma", "2"])}
 
 
