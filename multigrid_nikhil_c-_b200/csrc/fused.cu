@@ -27,6 +27,8 @@ static int g_tile_maxN = 1024;
 static bool g_autotune = true;   // MGB200_AUTOTUNE=0 disables the chunk-height tuner
 static int g_occ = 12;  // resident streaming warps per SM (MGB200_STREAM_OCC), enforced by padding dynamic shared memory
 
+void fused_setup_optin(Ctx& ctx);   // attributes of the opt-in kernels (defined below, next to them)
+
 template <typename T, int NS, int MODE, bool RBGS>
 static void set_attr()
 {
@@ -73,6 +75,7 @@ void fused_setup(Ctx& ctx)
     g_ctail_ctas = std::max(1, std::min(kCtailMaxCtas, env_int("MGB200_CTAIL_CTAS", 16)));
     if (ctx.f64()) set_attrs_t<double>();
     else set_attrs_t<float>();
+    fused_setup_optin(ctx);
 }
 
 // ---------------------------------------------------------------------------------
@@ -836,6 +839,62 @@ static bool comm_avoid_cycle(Ctx& ctx, int level, int nu1, int nu2, int gamma)
     if (ctx.f64()) comm_avoid_run<double>(ctx, plan, nu1, nu2);
     else comm_avoid_run<float>(ctx, plan, nu1, nu2);
     return true;
+}
+
+// The opt-in kernels opt into large dynamic shared memory (and the cluster kernel into a non-portable cluster size).
+// Do that once per context, OUTSIDE any stream capture; the launch sites keep a lazy fallback.
+template <typename T, int NS, int MODE, bool RBGS>
+static void tile_attrs()
+{
+    MG_CK(cudaFuncSetAttribute(k_tile<T, NS, MODE, RBGS, 16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)((size_t)TileCfg<T, NS, MODE, 16, 32>::SMEM_ELEMS * sizeof(T))));
+    MG_CK(cudaFuncSetAttribute(k_tile<T, NS, MODE, RBGS, 32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)((size_t)TileCfg<T, NS, MODE, 32, 64>::SMEM_ELEMS * sizeof(T))));
+}
+
+template <typename T>
+static void optin_attrs(Ctx& ctx)
+{
+    const int big = 100 * 1024;
+    if (ctx.chain) {
+        MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        MG_CK(cudaFuncSetAttribute(k_stream_fmg_entry<T, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        MG_CK(cudaFuncSetAttribute(k_stream_fmg_entry<T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        MG_CK(cudaFuncSetAttribute(k_stream_fmg_entry<T, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        MG_CK(cudaFuncSetAttribute(k_stream_fmg_entry<T, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    }
+    if (ctx.zero_guess) {
+        MG_CK(cudaFuncSetAttribute(k_stream_pre_zg<T, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        MG_CK(cudaFuncSetAttribute(k_stream_pre_zg<T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        MG_CK(cudaFuncSetAttribute(k_stream_pre_zg<T, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        MG_CK(cudaFuncSetAttribute(k_stream_pre_zg<T, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        const int ts = (int)tail_smem_bytes<T>(kTailMaxLevel, 1);
+        MG_CK(cudaFuncSetAttribute(k_tail_zg<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts));
+        MG_CK(cudaFuncSetAttribute(k_tail_zg<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts));
+    }
+    if (g_tile) {
+        tile_attrs<T, 1, TILE_PRE, false>();
+        tile_attrs<T, 2, TILE_PRE, false>();
+        tile_attrs<T, 1, TILE_POST, false>();
+        tile_attrs<T, 2, TILE_POST, false>();
+        tile_attrs<T, 2, TILE_PRE, true>();
+        tile_attrs<T, 4, TILE_PRE, true>();
+        tile_attrs<T, 2, TILE_POST, true>();
+        tile_attrs<T, 4, TILE_POST, true>();
+    }
+    if (g_ctail) {
+        MG_CK(cudaFuncSetAttribute(k_ctail<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MG_CK(cudaFuncSetAttribute(k_ctail<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    }
+}
+
+void fused_setup_optin(Ctx& ctx)
+{
+    if (ctx.f64()) optin_attrs<double>(ctx);
+    else optin_attrs<float>(ctx);
 }
 
 bool fused_cycle_level(Ctx& ctx, int level, int nu1, int nu2, int gamma)
