@@ -25,6 +25,7 @@ static int g_ctail_ctas = 16;    // MGB200_CTAIL_CTAS: cluster size (power of tw
 static bool g_tile = false;      // MGB200_TILE=1: shared-memory tile kernels on the mid levels (experimental, see tile.cuh)
 static int g_tile_maxN = 1024;
 static bool g_autotune = true;   // MGB200_AUTOTUNE=0 disables the chunk-height tuner
+static bool g_tma = false;       // MGB200_TMA=1: streaming kernels prefetch with bulk copies + mbarriers (experimental, stream.cuh)
 static int g_occ = 12;  // resident streaming warps per SM (MGB200_STREAM_OCC), enforced by padding dynamic shared memory
 
 void fused_setup_optin(Ctx& ctx);   // attributes of the opt-in kernels (defined below, next to them)
@@ -71,6 +72,7 @@ void fused_setup(Ctx& ctx)
     g_autotune = env_int("MGB200_AUTOTUNE", 1) != 0;
     g_tile = env_int("MGB200_TILE", 0) != 0;
     g_tile_maxN = env_int("MGB200_TILE_MAXN", 1024);
+    g_tma = env_int("MGB200_TMA", 0) != 0;
     g_ctail = env_int("MGB200_CTAIL", 0) != 0;
     g_ctail_ctas = std::max(1, std::min(kCtailMaxCtas, env_int("MGB200_CTAIL_CTAS", 16)));
     if (ctx.f64()) set_attrs_t<double>();
@@ -160,6 +162,9 @@ static void raw_launch(Ctx& ctx, const StreamArgs<T>& a)
     const size_t smem = std::min<size_t>(100 * 1024, std::max<size_t>(C::SMEM_BYTES, (size_t)(227 * 1024) / std::max(1, g_occ / kStreamWarps) - 1024));
     if constexpr (MODE == MODE_POSTPRE) {
         k_stream_chain<T, NS, RBGS><<<grid, kStreamWarps * 32, smem, ctx.stream>>>(a);
+    } else if (g_tma) {
+        const size_t smem_tma = std::max<size_t>(smem, C::SMEM_BYTES + kStreamTmaExtraSmem);
+        k_stream_tma<T, NS, MODE, RBGS><<<grid, kStreamWarps * 32, smem_tma, ctx.stream>>>(a);
     } else {
         k_stream<T, NS, MODE, RBGS><<<grid, kStreamWarps * 32, smem, ctx.stream>>>(a);
     }
@@ -852,10 +857,23 @@ static void tile_attrs()
                                (int)((size_t)TileCfg<T, NS, MODE, 32, 64>::SMEM_ELEMS * sizeof(T))));
 }
 
+template <typename T, int NS, int MODE, bool RBGS>
+static void tma_attr()
+{
+    MG_CK(cudaFuncSetAttribute(k_stream_tma<T, NS, MODE, RBGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+}
+
 template <typename T>
 static void optin_attrs(Ctx& ctx)
 {
     const int big = 100 * 1024;
+    if (g_tma) {   // the same instantiations as set_attrs_t
+        tma_attr<T, 1, MODE_SWEEPS, false>(); tma_attr<T, 2, MODE_SWEEPS, false>(); tma_attr<T, 3, MODE_SWEEPS, false>();
+        tma_attr<T, 4, MODE_SWEEPS, false>(); tma_attr<T, 1, MODE_PRE, false>(); tma_attr<T, 2, MODE_PRE, false>();
+        tma_attr<T, 1, MODE_POST, false>(); tma_attr<T, 2, MODE_POST, false>(); tma_attr<T, 2, MODE_SWEEPS, true>();
+        tma_attr<T, 4, MODE_SWEEPS, true>(); tma_attr<T, 2, MODE_PRE, true>(); tma_attr<T, 4, MODE_PRE, true>();
+        tma_attr<T, 2, MODE_POST, true>(); tma_attr<T, 4, MODE_POST, true>();
+    }
     if (ctx.chain) {
         MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));

@@ -119,9 +119,45 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 #endif
 
+// ---- TMA path (opt-in MGB200_TMA=1): 1-D bulk copies global -> shared (cp.async.bulk, SASS UBLKCP) completing on an
+//      mbarrier per ring slot, issued by ONE lane per row instead of a 16-byte cp.async by every lane ----
+#ifdef MGB_EMU
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)(uintptr_t)p; }
+__device__ __forceinline__ void mbar_init(void*, unsigned) {}
+__device__ __forceinline__ void mbar_init_fence() {}
+__device__ __forceinline__ void mbar_expect_tx(void*, unsigned) {}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, void*) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(void*, unsigned) {}
+__device__ __forceinline__ void fence_proxy_async() {}
+#else
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* mb, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(mb)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(void* mb, unsigned tx)
+{
+    asm volatile("mbarrier.arrive.expect_tx.relaxed.cta.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(mb)), "r"(tx) : "memory");
+}
+// size and both addresses are multiples of 16 bytes (host-checked geometry: pitch % 32 == 0, strip offsets % 8 == 0)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, void* mb)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(mb)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* mb, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\nMBW_TRY:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra MBW_DONE;\n\tbra MBW_TRY;\nMBW_DONE:\n}\n"
+                 ::"r"(smem_u32(mb)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+#endif
+
 // ZG ("zero guess"): the input iterate is known to be identically zero (first visit of a coarse level, P:613):
 // u is neither prefetched nor read, stage 0 is the constant 0.  Same arithmetic on the same values => same bits.
-template <typename T, int NS, int MODE, bool RBGS, bool ZG = false>
+// TMA: the prefetch uses bulk copies + mbarriers (above) instead of per-lane cp.async; everything else is unchanged.
+template <typename T, int NS, int MODE, bool RBGS, bool ZG = false, bool TMA = false>
 struct Streamer {
     typedef StreamCfg<T, NS, MODE> C;
     static constexpr int V = C::V;
@@ -147,6 +183,12 @@ struct Streamer {
     const T* safe_u;  // mapped addresses handed to ignored copies
     const T* safe_f;
     const T* safe_c;
+    // TMA path
+    unsigned long long* mbar;   // this warp's kRingSlots mbarriers (one per ring slot)
+    int it;                     // outer iteration (ring block) counter: slot set = it & 3, phase parity = (it >> 2) & 1
+    int lane_id, y_last;        // rows beyond y_last are never consumed and are not fetched
+    unsigned bytes_u, bytes_c;  // bytes of one row segment of this strip that exist in memory (the rest of a slot stays zero)
+    bool dead_;
 
     T W[C::NW > 0 ? C::NW : 1][3][V];
     T WL[C::NW > 0 ? C::NW : 1][3], WR[C::NW > 0 ? C::NW : 1][3];
@@ -178,6 +220,44 @@ struct Streamer {
     {
         constexpr int b = REL / 3, s = REL % 3;
         T* dst = blk[b & 3] + s * C::SLOT_ELEMS;
+        if constexpr (TMA) {
+            // warp-uniform validity of the whole row; lanes whose columns lie beyond the pitch keep the zeros of the
+            // initial fill (a bulk copy writes only the bytes_u bytes that exist)
+            const bool rv = !dead_ && (y >= a.row_lo) && (y < a.row_hi) && (y <= y_last);
+            bool cv = false;
+            T* cdst = nullptr;
+            if (C::HAS_POST) {
+                const int ic = (y + 1) >> 1;
+                cv = !dead_ && (ic >= a.crow_lo) && (ic < a.crow_hi) && (y >= 0) && (y <= y_last) && bytes_c > 0;
+                cdst = cblk[b & 3] + s * C::CSLOT_ELEMS;
+            }
+            if (!rv) {   // row outside the grid / the slab: zeros, written by every lane for its own 16 bytes
+                T z[V];
+#pragma unroll
+                for (int k = 0; k < V; ++k) z[k] = (T)0;
+                if (!ZG) stv<T>(dst, z);
+                stv<T>(dst + 32 * V, z);
+            }
+            if (C::HAS_POST && !cv) {
+#pragma unroll
+                for (int k = 0; k < H; ++k) cdst[k] = (T)0;
+            }
+            if (!rv || (C::HAS_POST && !cv)) fence_proxy_async();   // generic writes before later bulk writes to the slot
+            if (lane_id == 0) {
+                void* mb = mbar + (((it + b) & 3) * 3 + s);
+                const unsigned tx = (rv ? (ZG ? 1u : 2u) * bytes_u : 0u) + (cv ? bytes_c : 0u);
+                mbar_expect_tx(mb, tx);
+                if (rv) {
+                    if (!ZG) bulk_g2s(dst, g_u, bytes_u, mb);
+                    bulk_g2s(dst + 32 * V, g_f, bytes_u, mb);
+                }
+                if (cv) bulk_g2s(cdst, g_c, bytes_c, mb);
+            }
+            g_u += a.pitch;
+            g_f += a.pitch;
+            if (C::HAS_POST && !(y & 1)) g_c += a.pitch_c;
+            return;
+        }
         const bool v = lane_ld && (y >= a.row_lo) && (y < a.row_hi);
         if (!ZG) cp_async16(dst, v ? g_u : safe_u, v);
         cp_async16(dst + 32 * V, v ? g_f : safe_f, v);
@@ -404,6 +484,28 @@ struct Streamer {
             g_c = a.ec + (i64)((ylo + 1) >> 1) * a.pitch_c + (c >> 1);
         }
 
+        if constexpr (TMA) {
+            lane_id = lane;
+            dead_ = dead;
+            y_last = yhi;
+            it = 0;
+            const long long avail = (long long)a.pitch - X0;
+            bytes_u = (unsigned)(avail <= 0 ? 0 : (avail >= 32 * V ? 32 * V : avail)) * (unsigned)sizeof(T);
+            const long long availc = (long long)a.pitch_c - (X0 >> 1);
+            bytes_c = C::HAS_POST ? (unsigned)(availc <= 0 ? 0 : (availc >= 32 * H ? 32 * H : availc)) * (unsigned)sizeof(T) : 0u;
+            mbar = reinterpret_cast<unsigned long long*>(ring_base + (size_t)kStreamWarps * C::WARP_ELEMS) + warp * kRingSlots;
+            // the whole ring starts as zeros (columns beyond the pitch are never written by a bulk copy)
+            T* wbase = ring_base + (size_t)warp * C::WARP_ELEMS;
+            for (int i = lane; i < C::WARP_ELEMS; i += 32) wbase[i] = (T)0;
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < kRingSlots; ++i) mbar_init(mbar + i, 1);
+                mbar_init_fence();
+            }
+            fence_proxy_async();
+            __syncwarp();
+        }
+
         // prologue: rows ylo .. ylo+D-1 into slots 0 .. D-1
         set_blocks(0);
         issue_prologue<0>(ylo);
@@ -411,17 +513,29 @@ struct Streamer {
         for (int y = ylo; y <= yhi; y += 3) {
             set_blocks(q);
             issue<C::D>(y + C::D);
-            cp_async_wait<C::D>();
+            wait_row<0>();
             step<0>(y);
             issue<C::D + 1>(y + 1 + C::D);
-            cp_async_wait<C::D>();
+            wait_row<1>();
             step<1>(y + 1);
             issue<C::D + 2>(y + 2 + C::D);
-            cp_async_wait<C::D>();
+            wait_row<2>();
             step<2>(y + 2);
             q = (q + 1) & 3;
+            if constexpr (TMA) ++it;
         }
-        cp_async_wait<0>();
+        if constexpr (!TMA) cp_async_wait<0>();   // (TMA: nothing is fetched beyond the last consumed row)
+    }
+
+    // the row that step<PH> is about to consume has landed
+    template <int PH>
+    __device__ __forceinline__ void wait_row()
+    {
+        if constexpr (TMA) {
+            mbar_wait(mbar + ((it & 3) * 3 + PH), (unsigned)((it >> 2) & 1));
+        } else {
+            cp_async_wait<C::D>();
+        }
     }
 
     template <int I>
@@ -443,6 +557,19 @@ k_stream(const StreamArgs<T> a)
     const int item = blockIdx.x * kStreamWarps + warp;
     Streamer<T, NS, MODE, RBGS> st(a);
     st.run(reinterpret_cast<T*>(stream_smem), warp, threadIdx.x & 31, item);
+}
+
+// TMA variant (opt-in MGB200_TMA=1): same pipeline, rows arrive by bulk copy (UBLKCP) + mbarrier
+constexpr int kStreamTmaExtraSmem = 128;   // kStreamWarps * kRingSlots mbarriers after the rings
+template <typename T, int NS, int MODE, bool RBGS>
+__global__ void __launch_bounds__(kStreamWarps * 32, 12 / kStreamWarps)
+k_stream_tma(const StreamArgs<T> a)
+{
+    extern __shared__ __align__(128) unsigned char stream_tma_smem[];
+    const int warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * kStreamWarps + warp;
+    Streamer<T, NS, MODE, RBGS, false, true> st(a);
+    st.run(reinterpret_cast<T*>(stream_tma_smem), warp, threadIdx.x & 31, item);
 }
 
 // POSTPRE (visit chains, opt-in MGB200_CHAIN=1) needs ~142 registers at NS = 4: its own entry point with a launch bound

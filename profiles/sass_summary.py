@@ -55,7 +55,7 @@ def main():
     names = sorted(mix)
     pretty = dict(zip(names, demangle(names)))
     print("# Static SASS / ptxas summary of libmgb200.so (sm_100a, nvcc 12.9, -O3 --fmad=false); produced by profiles/sass_summary.py")
-    print("# cols: regs spill_B static_smem_B | instr LDG.128 STG.128 LDGSTS(cp.async) LDS STS SHFL DADD DMUL DFMA FADD FMUL FFMA BAR tensor(HMMA/UTC*MMA)")
+    print("# cols: regs spill_B static_smem_B | instr LDG.128 STG.128 LDGSTS(cp.async) UBLKCP(TMA) SYNCS(mbarrier) LDS STS SHFL DADD DMUL DFMA FADD FMUL FFMA BAR tensor(HMMA/UTC*MMA)")
     tot_tensor = 0
     for n in sorted(names, key=lambda k: pretty[k]):
         o = mix[n]
@@ -66,6 +66,7 @@ def main():
               f"{count(o, lambda k: k.startswith('LDG') and '.128' in k and not k.startswith('LDGSTS')):4d} "
               f"{count(o, lambda k: k.startswith('STG') and '.128' in k):4d} "
               f"{count(o, lambda k: k.startswith('LDGSTS')):4d} "
+              f"{count(o, lambda k: k.startswith('UBLKCP')):4d} {count(o, lambda k: k.startswith('SYNCS')):4d} "
               f"{count(o, lambda k: k.startswith('LDS')):4d} {count(o, lambda k: k.startswith('STS')):4d} "
               f"{count(o, lambda k: k.startswith('SHFL')):4d} "
               f"{count(o, lambda k: k.startswith('DADD')):4d} {count(o, lambda k: k.startswith('DMUL')):4d} {count(o, lambda k: k.startswith('DFMA')):4d} "

@@ -143,6 +143,32 @@ def test_visit_chain_postpre_bitwise(mgb, orc, knob, level, dtype, smoother, nu1
                 assert_bitwise(mg.get_u(level), orc.fullmultigrid(b, 1, pv), "resident fmg")
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("smoother,nu1,nu2,gamma", [("jacobi", 2, 2, 1), ("jacobi", 1, 1, 2), ("jacobi", 3, 5, 1), ("rbgs", 2, 2, 1), ("rbgs", 1, 1, 2)])
+@pytest.mark.parametrize("level", [3, 6, 7, 9, 10])
+def test_tma_streaming_kernels_bitwise(mgb, orc, knob, level, dtype, smoother, nu1, nu2, gamma):
+    """MGB200_TMA=1: the streaming kernels fetch rows with 1-D bulk copies (cp.async.bulk, UBLKCP) completing on one
+    mbarrier per ring slot instead of per-lane cp.async.  Same pipeline, same bits.  (On a GPU run this first, alone,
+    under a short timeout: a wrong transaction count would hang the kernel.)"""
+    knob("MGB200_TMA", "1")
+    x, b = rand_vec(level, dtype, 89), rand_vec(level, dtype, 90, 1e-3)
+    p = oracle.Params(nu1=nu1, nu2=nu2, gamma=gamma, smoother=1 if smoother == "rbgs" else 0, nthreads=4)
+    want = [x]
+    for _ in range(2):
+        want.append(orc.vcyclemultigrid(want[-1], b, p))
+    for graph, tail in ((False, False), (True, True)):
+        with mgb.Multigrid(level, dtype=dtype, smoother=smoother, graph=graph, coarse_tail=tail) as mg:
+            mg.set_u(level, x)
+            mg.set_rhs(level, b)
+            for k in range(2):
+                mg.cycle(level, nu1, nu2, gamma)
+                assert_bitwise(mg.get_u(level), want[k + 1], f"tma cycle {k + 1} graph={graph} tail={tail}")
+            mg.set_u(level, x)
+            mg.smooth(level, 3)
+            ref = orc.jacobirelaxation(x, b, 3) if smoother == "jacobi" else orc.rbgs(x, b, 3)
+            assert_bitwise(mg.get_u(level), ref, "tma sweeps")
+
+
 def test_visit_chain_really_fuses(mgb, knob):
     """Launch counts: 3 chained V(2,2) cycles at 513^2 save two launches on the finest level, a W-cycle one per level."""
     counts = {}

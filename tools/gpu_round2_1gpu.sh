@@ -17,6 +17,10 @@ MGB200_TEST_OPTIN=1 timeout 600 python -m pytest tests/test_optin_gpu.py -m gpu 
     > $O/r02_pytest_optin.log 2>&1; echo "rc=$?" >> $O/r02_pytest_optin.log
 tail -3 $O/r02_pytest_optin.log
 
+step "TMA variant of the streaming kernels, alone and under a short timeout (a wrong mbarrier transaction count would hang)"
+MGB200_TEST_OPTIN=1 timeout 180 python -m pytest tests/test_optin_gpu.py -m gpu -x -q -k "tma_streaming" > $O/r02_pytest_tma.log 2>&1; echo "rc=$?" >> $O/r02_pytest_tma.log
+tail -3 $O/r02_pytest_tma.log
+
 run_bench() {   # tag, env assignments...
     local tag=$1; shift
     env "$@" timeout 300 python bench.py --no-cpu --no-e2e --steps 20 --warmup 5 > $O/r02_bench_$tag.json 2> $O/r02_bench_$tag.err
@@ -42,6 +46,7 @@ run_bench ctail8 MGB200_CTAIL=1 MGB200_CTAIL_CTAS=8
 run_bench zg_tile MGB200_ZERO_GUESS=1 MGB200_TILE=1
 run_bench zg_ctail16 MGB200_ZERO_GUESS=1 MGB200_CTAIL=1
 run_bench zg_tile_ctail16 MGB200_ZERO_GUESS=1 MGB200_TILE=1 MGB200_CTAIL=1
+grep -q "rc=0" $O/r02_pytest_tma.log && run_bench tma MGB200_TMA=1
 run_bench chain MGB200_CHAIN=1
 run_bench chain_zg MGB200_CHAIN=1 MGB200_ZERO_GUESS=1
 run_bench chain_zg_tile_ctail16 MGB200_CHAIN=1 MGB200_ZERO_GUESS=1 MGB200_TILE=1 MGB200_CTAIL=1
