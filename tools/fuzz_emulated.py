@@ -33,7 +33,7 @@ def main():
         nu1, nu2 = int(rng.integers(0, 5)), int(rng.integers(0, 5))
         gamma = int(rng.integers(1, 4))
         flags = dict(graph=bool(rng.integers(0, 2)), fused=bool(rng.integers(0, 2)), coarse_tail=bool(rng.integers(0, 2)))
-        env = {k: str(int(rng.integers(0, 2))) for k in ("MGB200_TILE", "MGB200_ZERO_GUESS", "MGB200_CTAIL", "MGB200_CHAIN")}
+        env = {k: str(int(rng.integers(0, 2))) for k in ("MGB200_TILE", "MGB200_ZERO_GUESS", "MGB200_CTAIL", "MGB200_CHAIN", "MGB200_TMA")}
         env["MGB200_CTAIL_CTAS"] = str([1, 2, 4, 8, 16][int(rng.integers(0, 5))])
         if os.environ.get("FUZZ_DEFAULT_ONLY") == "1":
             env = {k: "0" for k in env}
