@@ -157,6 +157,27 @@ def test_config0_solve_257_matches_reference_history(mgb, orc, smoother, gamma, 
         assert_bitwise(mg.get_u(level), u, "solution")
 
 
+@pytest.mark.parametrize("smoother,gamma", [("jacobi", 1), ("rbgs", 2)])
+def test_mg_cycles_equals_repeated_cycles(mgb, orc, smoother, gamma):
+    """mg_cycles(count) == the loop P:646-648 of `count` vcyclemultigrid calls, bit for bit (one graph for the run)."""
+    level = 7
+    x, b = rand_vec(level, np.float64, 51), rand_vec(level, np.float64, 52, 1e-3)
+    p = oracle.Params(smoother=1 if smoother == "rbgs" else 0, gamma=gamma, nthreads=4)
+    want = x
+    for _ in range(4):
+        want = orc.vcyclemultigrid(want, b, p)
+    for graph in (False, True):
+        with make(mgb, level, smoother=smoother, graph=graph) as mg:
+            mg.set_u(level, x)
+            mg.set_rhs(level, b)
+            mg.cycles(3, level, 2, 2, gamma)
+            mg.cycles(1, level, 2, 2, gamma)
+            mg.cycles(0, level, 2, 2, gamma)
+            assert_bitwise(mg.get_u(level), want, f"mg_cycles graph={graph}")
+            with pytest.raises(mgb.capi.MgError):
+                mg.cycles(-1, level)
+
+
 def test_golden_fixtures(mgb):
     """Committed oracle outputs (tests/golden/oracle_golden.npz, made by make_golden.py)."""
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.npz"))
