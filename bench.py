@@ -150,10 +150,21 @@ class GpuLocalAffinity:
                 pass
 
 
-def pinned(nelem: int, dtype):
+NUMA_CPUS = None   # CPUs the last pinned allocation was bound to (None: no binding happened)
+
+
+def pinned(nelem: int, dtype, device=None):
+    """Pinned host buffer; with `device` given it is allocated while the thread is bound to that GPU's local CPUs, so
+    the pages land on the GPU's NUMA node.  The binding covers only the allocation call."""
+    global NUMA_CPUS
     import torch
-    t = torch.empty(nelem, dtype={np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}[np.dtype(dtype)],
-                    pin_memory=torch.cuda.is_available())
+    tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}[np.dtype(dtype)]
+    if device is None:
+        t = torch.empty(nelem, dtype=tdt, pin_memory=torch.cuda.is_available())
+    else:
+        with GpuLocalAffinity(device) as aff:
+            t = torch.empty(nelem, dtype=tdt, pin_memory=torch.cuda.is_available())
+            NUMA_CPUS = aff.cpus
     return t, t.numpy()
 
 
@@ -263,25 +274,22 @@ def run_ours(args, rank, world, local_rank):
                           comm_id=comm, graph=not args.no_graph, fused=not args.no_fused,
                           coarse_tail=not args.no_tail, agglomerate_level=args.aggl)
     slab = world > 1 and not args.full_host_vectors
-    numa = GpuLocalAffinity(local_rank)
-    numa.__enter__()           # host buffers below are allocated and first touched on the GPU's NUMA node
     if slab:
         # a rank only ever touches the interior rows it stores: keep just those on the host (Multigrid.set_rhs_slab)
         ya, yb = mg.slab_rows(level)
-        f_t, f_host = pinned((yb - ya) * n, dtype)
-        u_t, u_host = pinned((yb - ya) * n, dtype)
+        f_t, f_host = pinned((yb - ya) * n, dtype, local_rank)   # on the GPU's NUMA node
+        u_t, u_host = pinned((yb - ya) * n, dtype, local_rank)
         h = 1.0 / (1 << level)
         rng = np.random.default_rng(1234 + ya)          # depends on the rows, not on the rank count
         f_host[:] = (h * h * rng.uniform(-1.0, 1.0, (yb - ya) * n)).astype(dtype)
         u_host[:] = 0
         mg.set_rhs_slab(level, f_host)
     else:
-        f_t, f_host = pinned(n * n, dtype)
-        u_t, u_host = pinned(n * n, dtype)
+        f_t, f_host = pinned(n * n, dtype, local_rank)           # on the GPU's NUMA node
+        u_t, u_host = pinned(n * n, dtype, local_rank)
         f_host[:] = synthetic_rhs(level, dtype)
         u_host[:] = 0
         mg.set_rhs(level, f_host)
-    numa.__exit__()
     mg.zero_u(level)
     upd = updates_per_cycle(level, 1, nu1, nu2, gamma)
 
@@ -387,7 +395,7 @@ def run_ours(args, rank, world, local_rank):
            "h2d_bytes_per_step": 2 * (n if world == 1 else mg.slab_rows(level)[1] - mg.slab_rows(level)[0]) * n * esize,
            "d2h_bytes_per_step": rows * n * esize,
            "call": "mg_host_vcyclemultigrid (vcyclemultigrid P:575 on pinned host vectors)",
-           "host_buffers_on_gpu_numa_node_cpus": numa.cpus}
+           "host_buffers_on_gpu_numa_node_cpus": NUMA_CPUS}
 
     # informational: the reference's top-level call shape, fullmultigrid(f_h) -> u (P:629 / main P:727): one H2D of f,
     # one V(2,2) per level on the way up, one D2H of u.  Transfers are amortised over ~4/3 cycles' worth of work.

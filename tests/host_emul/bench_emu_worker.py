@@ -27,7 +27,7 @@ _init = dist.init_process_group
 dist.init_process_group = lambda backend, **kw: _init("gloo")
 _tensor = torch.tensor
 torch.tensor = lambda data, **kw: _tensor(data, **{k: v for k, v in kw.items() if k != "device"})
-bench.pinned = lambda nelem, dtype: (None, np.empty(nelem, dtype=dtype))
+bench.pinned = lambda nelem, dtype, device=None: (None, np.empty(nelem, dtype=dtype))
 
 
 def main():

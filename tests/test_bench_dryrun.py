@@ -101,7 +101,7 @@ def test_bench_control_flow_and_json_contract(monkeypatch, world):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
     monkeypatch.setattr(mgb200, "Multigrid", StubMG)
     monkeypatch.setattr(mgb200, "comm_id", lambda: bytes(128))
-    monkeypatch.setattr(bench, "pinned", lambda nelem, dtype: (None, np.empty(nelem, dtype=dtype)))
+    monkeypatch.setattr(bench, "pinned", lambda nelem, dtype, device=None: (None, np.empty(nelem, dtype=dtype)))
     monkeypatch.setattr(bench, "ClockSampler", lambda dev: type("S", (), {"start": lambda s: None, "stop": lambda s: {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 1}})())
     if world > 1:
         import torch.distributed as dist
