@@ -148,3 +148,25 @@ def test_micro_benchmark_line(monkeypatch, capsys):
     d = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert d["metric"] == "smoother_point_updates_per_s" and d["dtype"] == "f32"
     assert "jacobi_k2_one_launch" in d["roofline"]["kernels"] and d["roofline"]["frac"] > 0
+
+
+def test_gpu_local_affinity_binds_and_restores(monkeypatch):
+    """bench.GpuLocalAffinity: bound to the GPU's CPUs inside, previous mask restored outside, silent without NVML."""
+    import os
+    import sys
+    import types
+    allowed = sorted(os.sched_getaffinity(0))
+    if len(allowed) < 2:
+        pytest.skip("needs two CPUs")
+    fake = types.ModuleType("pynvml")
+    fake.nvmlInit = lambda: None
+    fake.nvmlDeviceGetHandleByIndex = lambda i: i
+    fake.nvmlDeviceGetCpuAffinity = lambda h, n: [1 << (allowed[0] % 64) if i == allowed[0] // 64 else 0 for i in range(n)]
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    before = os.sched_getaffinity(0)
+    with bench.GpuLocalAffinity(0) as a:
+        assert os.sched_getaffinity(0) == {allowed[0]} and a.cpus == 1
+    assert os.sched_getaffinity(0) == before
+    fake.nvmlDeviceGetCpuAffinity = lambda h, n: (_ for _ in ()).throw(RuntimeError("no NVML"))
+    with bench.GpuLocalAffinity(0) as a:
+        assert os.sched_getaffinity(0) == before and a.cpus is None
