@@ -422,6 +422,23 @@ def run_ours(args, rank, world, local_rank):
         except Exception as ex:  # noqa: BLE001 - informational leg only
             e2e["fullmultigrid_call"] = {"error": str(ex)}
 
+    # tolerance-controlled solve on the same right-hand side (the reference runs a fixed number of cycles
+    # and prints only the vector length): cycle count, residual history, wall time incl. the per-cycle norm read-back
+    solve_info = None
+    try:
+        mg.zero_u(level)
+        mg.sync()
+        barrier()
+        t0 = time.perf_counter()
+        k_cyc, relres, hist = mg.solve(1e-8, 40, nu1, nu2, gamma)
+        mg.sync()
+        solve_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        solve_info = {"rtol": 1e-8, "cycles": k_cyc, "relres": relres, "ms": solve_ms,
+                      "residual_history": [float(h) for h in hist],
+                      "factors": [float(hist[i + 1] / hist[i]) for i in range(len(hist) - 1) if hist[i] > 0]}
+    except Exception as ex:  # noqa: BLE001 - informational leg only
+        solve_info = {"error": str(ex)}
+
     # N > 1: the same workload on ONE GPU (rank 0 alone, resident data, same flags), so that the strong-scaling
     # denominator for this grid size is in the same line (bench.py --gpus 1 measures BASELINE configs[1], 4097^2)
     n1 = None
@@ -460,6 +477,7 @@ def run_ours(args, rank, world, local_rank):
     if os.environ.get("MGB200_CHAIN") == "1":
         # with visit chains the K timed cycles share POST+PRE launches on the finest level; also report one isolated cycle
         line["isolated_cycle_ms"] = statistics.median([mg.time_cycle(level, nu1, nu2, gamma, 1) for _ in range(20)])
+    line["solve"] = solve_info
     if n1 is not None:
         line["n1_same_workload"] = n1
     if rank == 0 and world == 1 and not args.no_cpu:

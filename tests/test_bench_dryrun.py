@@ -70,6 +70,9 @@ class StubMG:
     def fmg(self, cycles, nu1, nu2):
         pass
 
+    def solve(self, rtol, max_cycles, nu1, nu2, gamma):
+        return 3, 1e-9, np.array([1.0, 1e-3, 1e-6, 1e-9])
+
     def sync(self):
         pass
 
