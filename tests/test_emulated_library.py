@@ -153,6 +153,7 @@ def test_bench_harness_end_to_end_under_emulation(jobs, name):
     assert d["n_gpus"] == world and d["gpu_launches"] > 0 and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
     assert d["roofline"]["achieved"] > 0 and set(["bound", "peak", "unit", "frac", "traffic"]) <= set(d["roofline"])
+    assert d["solve"]["cycles"] > 0 and d["solve"]["relres"] <= 1e-8 and len(d["solve"]["residual_history"]) == d["solve"]["cycles"] + 1
     if world > 1:   # the strong-scaling denominator: same grid on one rank
         assert d["n1_same_workload"]["ms_per_step"] > 0 and "error" not in d["n1_same_workload"]
 
