@@ -279,9 +279,12 @@ def run_ours(args, rank, world, local_rank):
         ya, yb = mg.slab_rows(level)
         f_t, f_host = pinned((yb - ya) * n, dtype, local_rank)   # on the GPU's NUMA node
         u_t, u_host = pinned((yb - ya) * n, dtype, local_rank)
+        # one generator per GLOBAL row: every rank holds the same values for a row it stores (its halo rows are the
+        # neighbour's owned rows), and the right-hand side does not depend on the number of ranks
         h = 1.0 / (1 << level)
-        rng = np.random.default_rng(1234 + ya)          # depends on the rows, not on the rank count
-        f_host[:] = (h * h * rng.uniform(-1.0, 1.0, (yb - ya) * n)).astype(dtype)
+        fv = f_host.reshape(yb - ya, n)
+        for i, row in enumerate(range(ya, yb)):
+            fv[i] = (h * h * np.random.default_rng([1234, row]).uniform(-1.0, 1.0, n)).astype(dtype)
         u_host[:] = 0
         mg.set_rhs_slab(level, f_host)
     else:
@@ -464,7 +467,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": f"{n + 2}^2 {'fp64' if esize == 8 else 'fp32'} V({nu1},{nu2}) gamma={gamma} "
                                    f"{args.smoother}, full weighting / bilinear, coarsened to 3x3"
                                    + ("" if world == 1 else f", row slabs over {world} GPUs"),
-                       "level": level, "rhs": "h^2*U(-1,1) rng(1234)" if not slab else "h^2*U(-1,1), rng seeded per row slab", "updates_per_cycle": upd,
+                       "level": level, "rhs": "h^2*U(-1,1) rng(1234)" if not slab else "h^2*U(-1,1), rng seeded per global row", "updates_per_cycle": upd,
                        "l2_policy": "inputs larger than L2 (4 arrays x %.0f MB on the finest level)" % (n * n * esize / 1e6),
                        "regions": regions, "region_stat": "median", "agglomerate_level": mg.info(capi.MG_INFO_AGGLOMERATE_LEVEL, level) if world > 1 else None,
                        "timed_as": f"{K} consecutive cycles per region through mg_time_cycle (mg_cycles)",
