@@ -60,7 +60,7 @@ class Jobs:
     run side by side (the emulation is single-threaded per rank), each test then waits for its own."""
 
     def __init__(self, tmp):
-        self.tmp, self.procs = tmp, None
+        self.tmp, self.procs, self.done = tmp, None, {}
 
     def start(self):
         self.procs = {}
@@ -86,9 +86,12 @@ class Jobs:
     def result(self, name, timeout=1500):
         if self.procs is None:
             self.start()
-        p = self.procs[name]
-        out, err = p.communicate(timeout=timeout)
-        assert p.returncode == 0, out[-3000:] + err[-3000:]
+        if name not in self.done:
+            p = self.procs[name]
+            out, err = p.communicate(timeout=timeout)
+            self.done[name] = (p.returncode, out, err)
+        rc, out, err = self.done[name]
+        assert rc == 0, out[-3000:] + err[-3000:]
         return out
 
 
@@ -131,7 +134,8 @@ def test_two_rank_row_slabs_under_emulation(jobs, name):
     if KNOBS[name].get("MGB200_COMM_AVOID") == "1":
         # the communication-avoiding plan really ran: far fewer point-to-point messages than the default schedule
         sends = int(out.split("sends=")[1].split()[0])
-        assert sends < 800, out[-500:]
+        default_sends = int(jobs.result("slabs:default").split("sends=")[1].split()[0])
+        assert sends < 0.75 * default_sends, (sends, default_sends)
 
 
 BENCH_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
