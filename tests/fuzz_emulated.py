@@ -1,6 +1,6 @@
 """Randomised parity check of the whole library against the oracle on the CPU emulation build (tests/host_emul):
 random levels, coarsest levels, sweep counts, cycle index, smoother, dtype, flags and call sequences.
-    python tools/fuzz_emulated.py [seconds] [seed]
+    python tests/fuzz_emulated.py [seconds] [seed]
 TEST TOOLING; prints the failing configuration and exits 1 on the first mismatch."""
 import os
 import sys
