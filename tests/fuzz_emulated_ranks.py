@@ -48,6 +48,8 @@ def main():
         nu1, nu2, gamma = int(rng.integers(0, 4)), int(rng.integers(0, 4)), int(rng.integers(1, 3))
         flags = dict(graph=bool(rng.integers(0, 2)), fused=bool(rng.integers(0, 4) > 0), coarse_tail=bool(rng.integers(0, 2)))
         env = {k: str(int(rng.integers(0, 2))) for k in KNOBS}
+        if os.environ.get("FUZZ_DEFAULT_ONLY") == "1":      # the default configuration only (what the GPU suite runs)
+            env = {k: "0" for k in KNOBS}
         os.environ.update(env)
         cfg = dict(level=level, aggl=aggl, dtype=np.dtype(dtype).name, smoother=smoother, nu1=nu1, nu2=nu2, gamma=gamma, **flags, **env)
         m = (1 << level) - 1
