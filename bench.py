@@ -336,12 +336,13 @@ def run_ours(args, rank, world, local_rank):
         gbs = s_per_pt * esize * pts / (t * 1e-3) / 1e9
         kernels[name] = {"ms": t, "algorithmic_bytes": s_per_pt * esize * pts, "GBps": gbs, "frac_of_peak": gbs / peak}
     for name, op, s_per_pt in (("pre_fused(2 sweeps+residual+restrict)", capi.MG_OP_PRE_FUSED, 3.25),
-                               ("post_fused(prolong+correct+2 sweeps)", capi.MG_OP_POST_FUSED, 3.25)):
+                               ("post_fused(prolong+correct+2 sweeps)", capi.MG_OP_POST_FUSED, 3.25),
+                               ("postpre_chain(prolong+correct+4 sweeps+residual+restrict)", capi.MG_OP_POSTPRE_FUSED, 3.5)):
         try:
             t = mg.time_op(op, level, reps) / reps
         except capi.MgError:
             continue
-        unfused = (2 * 3 + 3 + 1.25) if "pre" in name else (2.25 + 2 * 3)
+        unfused = (2.25 + 4 * 3 + 3 + 1.25) if "chain" in name else ((2 * 3 + 3 + 1.25) if "pre" in name else (2.25 + 2 * 3))
         kernels[name] = {"ms": t, "algorithmic_bytes": s_per_pt * esize * pts,
                          "GBps": s_per_pt * esize * pts / (t * 1e-3) / 1e9,
                          "frac_of_peak": s_per_pt * esize * pts / (t * 1e-3) / 1e9 / peak,

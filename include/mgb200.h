@@ -132,7 +132,8 @@ int mg_time_op(mg_ctx* ctx, int op, int level, int reps, float* ms_out);
 int mg_time_cycle(mg_ctx* ctx, int level, int nu1, int nu2, int gamma, int reps, float* ms_out);
 enum { MG_OP_SMOOTH1 = 0, MG_OP_RESIDUAL = 1, MG_OP_RESTRICT = 2, MG_OP_PROLONG = 3,
        MG_OP_PRE_FUSED = 4, MG_OP_POST_FUSED = 5, MG_OP_RESIDUAL_NORM = 6, MG_OP_SMOOTH2 = 7,
-       MG_OP_SMOOTH3 = 8, MG_OP_SMOOTH4 = 9 /* k sweeps temporally blocked in ONE launch (k = 4: Jacobi only) */ };
+       MG_OP_SMOOTH3 = 8, MG_OP_SMOOTH4 = 9, /* k sweeps temporally blocked in ONE launch (k = 4: Jacobi only) */
+       MG_OP_POSTPRE_FUSED = 10 /* POST + PRE of consecutive visits in one launch (needs MGB200_CHAIN=1) */ };
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ MG_COMM_ID_BYTES = 128
  MG_INFO_DISTRIBUTED, MG_INFO_BYTES_ALLOCATED, MG_INFO_GRAPH_LAUNCHES, MG_INFO_AGGLOMERATE_LEVEL,
  MG_INFO_STORED_ROW_BEGIN, MG_INFO_STORED_ROW_END) = range(11)
 (MG_OP_SMOOTH1, MG_OP_RESIDUAL, MG_OP_RESTRICT, MG_OP_PROLONG, MG_OP_PRE_FUSED, MG_OP_POST_FUSED,
- MG_OP_RESIDUAL_NORM, MG_OP_SMOOTH2, MG_OP_SMOOTH3, MG_OP_SMOOTH4) = range(10)
+ MG_OP_RESIDUAL_NORM, MG_OP_SMOOTH2, MG_OP_SMOOTH3, MG_OP_SMOOTH4, MG_OP_POSTPRE_FUSED) = range(11)
 
 
 class MgConfig(ctypes.Structure):

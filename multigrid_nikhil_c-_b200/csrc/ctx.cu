@@ -577,6 +577,9 @@ float Ctx::time_op(int op, int level, int reps)
             case MG_OP_POST_FUSED:
                 if (!fused_time_hook(*this, level, false)) throw MgError(MG_ERR_STATE, "fused post-smoothing kernel not available for this level/config");
                 break;
+            case MG_OP_POSTPRE_FUSED:
+                if (!fused_time_hook_postpre(*this, level)) throw MgError(MG_ERR_STATE, "POST+PRE chain kernel not available (MGB200_CHAIN=1, fused, this level/config)");
+                break;
             default: throw MgError(MG_ERR_ARG, "unknown op");
         }
     };

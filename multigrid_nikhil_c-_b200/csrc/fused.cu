@@ -1016,6 +1016,19 @@ bool fused_time_sweeps4(Ctx& ctx, int level)
     return true;
 }
 
+bool fused_time_hook_postpre(Ctx& ctx, int level)
+{
+    if (level <= ctx.cfg.coarsest_level) return false;
+    Level& lv = ctx.L(level);
+    Level& lcv = ctx.L(level - 1);
+    const int nu = ctx.cfg.smoother == MG_SMOOTH_JACOBI ? 2 : 1;
+    const int ns = postpre_ns(ctx, lv, nu, nu);
+    if (ns == 0) return false;
+    if (ctx.f64()) postpre_fused<double>(ctx, lv, lcv, ns, nu);
+    else postpre_fused<float>(ctx, lv, lcv, ns, nu);
+    return true;
+}
+
 bool fused_time_hook(Ctx& ctx, int level, bool pre)
 {
     if (level <= ctx.cfg.coarsest_level) return false;

@@ -18,6 +18,8 @@ bool fused_cycle_chain(Ctx& ctx, int level, int nu1, int nu2, int gamma, int vis
 void fused_pretune(Ctx& ctx, int level, int nu1, int nu2, int gamma);
 // one launch of the fused pre- (true) or post-smoothing (false) kernel for timing; false if unavailable
 bool fused_time_hook(Ctx& ctx, int level, bool pre);
+// one launch of the POST+PRE chain kernel (nu2 = nu1 = 2 Jacobi / 1 RB-GS) for timing; false if unavailable
+bool fused_time_hook_postpre(Ctx& ctx, int level);
 // micro-benchmark only: four weighted-Jacobi sweeps temporally blocked in one launch (not used by the cycles)
 bool fused_time_sweeps4(Ctx& ctx, int level);
 
