@@ -83,6 +83,15 @@ enum { MG_INFO_PITCH = 0, MG_INFO_ROWS_STORED = 1, MG_INFO_ROW_BEGIN = 2, MG_INF
  *      takes / fills the rows of its slab (mg_get_* gathers nothing across ranks:
  *      rows outside the slab are left untouched) ---- */
 int mg_force_constant(mg_ctx* ctx, double f);                      /* globalforcefunction P:283-335: b = f*h^2 on the finest level */
+/* Synthetic right-hand side for benchmarks, generated on the device (no reference counterpart; the reference only has the
+ * constant f = 4, P:123): b = h^2 (2U - 1), U = (splitmix64(seed + (idx+1)*0x9E3779B97F4A7C15) >> 11) * 2^-53, idx = the
+ * reference's interior index (row-1)*n + (col-1) (P:227-228).  A function of the GLOBAL index only: every rank of a
+ * row-slab run and a single-GPU run of the same grid hold identical values (tests restate it in numpy). */
+int mg_force_synthetic(mg_ctx* ctx, uint64_t seed);
+/* Order-independent 64-bit checksum of this rank's OWNED interior values of u (which = 0), f (1) or r (2) on `level`:
+ * sum mod 2^64 of splitmix64(value bits + (idx+1)*0x9E37...) over the points.  The sum over the ranks of a row-slab run
+ * equals the single-GPU checksum exactly when every value agrees bit for bit (bench.py's multi-GPU parity record). */
+int mg_checksum(mg_ctx* ctx, int level, int which, uint64_t* out);
 int mg_set_rhs_host(mg_ctx* ctx, int level, const void* f_host);   /* f_h argument of P:575 / P:629 */
 int mg_set_u_host(mg_ctx* ctx, int level, const void* u_host);     /* vec_h argument of P:575       */
 int mg_get_u_host(mg_ctx* ctx, int level, void* u_host);           /* returned vector P:626, P:649  */

@@ -82,6 +82,8 @@ def lib() -> ctypes.CDLL:
         "mg_slab_rows": (ci, [ci, ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]),
         "mg_get_info": (ci, [vp, ci, ci, ctypes.POINTER(ctypes.c_int64)]),
         "mg_force_constant": (ci, [vp, cd]),
+        "mg_force_synthetic": (ci, [vp, ctypes.c_uint64]),
+        "mg_checksum": (ci, [vp, ci, ci, ctypes.POINTER(ctypes.c_uint64)]),
         "mg_set_rhs_host": (ci, [vp, ci, vp]),
         "mg_set_u_host": (ci, [vp, ci, vp]),
         "mg_get_u_host": (ci, [vp, ci, vp]),

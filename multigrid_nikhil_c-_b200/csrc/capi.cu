@@ -142,6 +142,14 @@ int mg_get_info(const mg_ctx* c, int what, int level, int64_t* out)
 }
 
 int mg_force_constant(mg_ctx* c, double f) { return guarded(c, [&](Ctx& x) { x.force_constant(f); }); }
+int mg_force_synthetic(mg_ctx* c, uint64_t seed) { return guarded(c, [&](Ctx& x) { x.force_synthetic(seed); }); }
+int mg_checksum(mg_ctx* c, int level, int which, uint64_t* out)
+{
+    return guarded(c, [&](Ctx& x) {
+        MG_REQUIRE(out != nullptr && which >= 0 && which <= 2, "null out or which not in {0 u, 1 f, 2 r}");
+        *out = x.checksum(level, (Ctx::Which)which);
+    });
+}
 int mg_set_rhs_host(mg_ctx* c, int level, const void* p) { return guarded(c, [&](Ctx& x) { x.set_host(level, Ctx::W_F, p); }); }
 int mg_set_u_host(mg_ctx* c, int level, const void* p) { return guarded(c, [&](Ctx& x) { x.set_host(level, Ctx::W_U, p); }); }
 int mg_get_u_host(mg_ctx* c, int level, void* p) { return guarded(c, [&](Ctx& x) { x.get_host(level, Ctx::W_U, p); }); }
@@ -278,16 +286,10 @@ int mg_time_cycle(mg_ctx* c, int level, int nu1, int nu2, int gamma, int reps, f
 {
     return guarded(c, [&](Ctx& x) {
         MG_REQUIRE(ms_out != nullptr && reps >= 1, "null ms_out or reps < 1");
-        cudaEvent_t e0, e1;
-        MG_CK(cudaEventCreate(&e0));
-        MG_CK(cudaEventCreate(&e1));
-        MG_CK(cudaEventRecord(e0, x.stream));
+        EventTimer t(x.stream);
+        t.start();
         x.cycles(level, nu1, nu2, gamma, reps);
-        MG_CK(cudaEventRecord(e1, x.stream));
-        MG_CK(cudaEventSynchronize(e1));
-        MG_CK(cudaEventElapsedTime(ms_out, e0, e1));
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
+        *ms_out = t.stop();
     });
 }
 

@@ -32,7 +32,20 @@ void slab_rows(int level, int rank, int world, int* lo, int* hi)
 
 static i64 round_up(i64 a, i64 m) { return (a + m - 1) / m * m; }
 
+// A constructor that throws does not run the destructor: everything acquired so far (stream, device arrays of the
+// levels already allocated, pinned buffers, communicator) is released here before the error leaves mg_create, so a
+// caller that retries with a smaller grid starts from a clean device.
 Ctx::Ctx(const mg_config& c) : cfg(c)
+{
+    try {
+        init();
+    } catch (...) {
+        release();
+        throw;
+    }
+}
+
+void Ctx::init()
 {
     MG_REQUIRE(cfg.finest_level >= 1 && cfg.finest_level <= 15, "finest_level must be in 1..15");
     MG_REQUIRE(cfg.coarsest_level >= 1 && cfg.coarsest_level <= cfg.finest_level,
@@ -125,9 +138,14 @@ Ctx::Ctx(const mg_config& c) : cfg(c)
         lv.r = (char*)lv.alloc[3] - off;
     }
     {
-        const Level& top = levels[cfg.finest_level];
+        // one partial per residual block; a replicated level below a distributed finest level stores more rows than the
+        // finest slab does, so the capacity is the maximum over all levels
         const int V = f64() ? 2 : 4;
-        partials_cap = (int)(cdiv(top.N, V * kTX) * cdiv(top.st_hi - top.st_lo, 2)) + 8;
+        partials_cap = 0;
+        for (int l = cfg.coarsest_level; l <= cfg.finest_level; ++l) {
+            const Level& lv = levels[l];
+            partials_cap = std::max(partials_cap, (int)(cdiv(lv.N, V * kTX) * cdiv(lv.st_hi - lv.st_lo, 2)) + 8);
+        }
         MG_CK(cudaMalloc(&d_partials, sizeof(double) * (size_t)partials_cap));
         MG_CK(cudaMalloc(&d_norm, sizeof(double) * 8));
         MG_CK(cudaMallocHost(&h_norm, sizeof(double) * 8));
@@ -145,23 +163,24 @@ Ctx::Ctx(const mg_config& c) : cfg(c)
         }
     }
     {
+        // both on by default (measured on the B200: profiles/r02a_*); "=0" switches one off for A/B timing
         const char* zg = getenv("MGB200_ZERO_GUESS");
-        zero_guess = zg && zg[0] == '1';
+        zero_guess = !(zg && zg[0] == '0');
         const char* ch = getenv("MGB200_CHAIN");
-        chain = ch && ch[0] == '1';
+        chain = !(ch && ch[0] == '0');
     }
     fused_setup(*this);
     MG_CK(cudaStreamSynchronize(stream));
 }
 
-Ctx::~Ctx()
+Ctx::~Ctx() { release(); }
+
+void Ctx::release() noexcept
 {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     for (auto& kv : graphs)
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-    for (auto& kv : ctail_ops)
-        if (kv.second.first) cudaFree(kv.second.first);
     if (comm_stream) cudaStreamSynchronize(comm_stream);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -174,6 +193,13 @@ Ctx::~Ctx()
     if (d_norm) cudaFree(d_norm);
     if (h_norm) cudaFreeHost(h_norm);
     if (stream) cudaStreamDestroy(stream);
+    graphs.clear();
+    levels.clear();
+    comm = nullptr;
+    comm_stream = nullptr;
+    ev_fork = ev_join = nullptr;
+    d_partials = d_norm = h_norm = nullptr;
+    stream = nullptr;
 }
 
 Level& Ctx::L(int level)
@@ -222,11 +248,11 @@ std::string Ctx::state_blob() const
     for (int l = cfg.coarsest_level; l <= cfg.finest_level; ++l) {
         const Level& lv = levels[l];
         b.push_back((char)(lv.cur | (lv.u_zero ? 2 : 0) | (lv.u_interp ? 4 : 0)));
-        if (lv.distributed) {
-            b.push_back((char)lv.hv_u);
-            b.push_back((char)lv.hv_f);
-            b.push_back((char)lv.hv_r);
-        }
+        if (lv.distributed)   // halo depths exceed 127 under the communication-avoiding schedule: 16 bits each
+            for (int hv : {lv.hv_u, lv.hv_f, lv.hv_r}) {
+                b.push_back((char)(hv & 0xff));
+                b.push_back((char)((hv >> 8) & 0xff));
+            }
     }
     return b;
 }
@@ -241,9 +267,10 @@ void Ctx::set_state(const std::string& blob)
         lv.u_interp = (blob[k] & 4) != 0;
         ++k;
         if (lv.distributed) {
-            lv.hv_u = blob[k++];
-            lv.hv_f = blob[k++];
-            lv.hv_r = blob[k++];
+            auto rd = [&]() { const int v = (unsigned char)blob[k] | ((unsigned char)blob[k + 1] << 8); k += 2; return v; };
+            lv.hv_u = rd();
+            lv.hv_f = rd();
+            lv.hv_r = rd();
         }
     }
 }
@@ -309,6 +336,34 @@ void Ctx::force_constant(double fval)
     else launch_fill<float>(stream, lc, (float*)lv.f, lv.pitch, lv.N, ya, yb, (float)b);
     MG_CK(cudaGetLastError());
     lv.hv_f = lv.halo;
+}
+
+void Ctx::force_synthetic(unsigned long long seed)
+{
+    Level& lv = L(cfg.finest_level);
+    const double h = 1.0 / (double)lv.N;
+    const int ya = std::max(lv.st_lo, 1), yb = std::min(lv.st_hi, lv.N);   // owned rows and halo rows alike
+    if (f64()) launch_fill_synthetic<double>(stream, lc, (double*)lv.f, lv.pitch, lv.N, ya, yb, h * h, seed);
+    else launch_fill_synthetic<float>(stream, lc, (float*)lv.f, lv.pitch, lv.N, ya, yb, h * h, seed);
+    MG_CK(cudaGetLastError());
+    lv.hv_f = lv.halo;
+}
+
+unsigned long long Ctx::checksum(int level, Which w)
+{
+    Level& lv = L(level);
+    if (w == W_U) materialize_u(lv);
+    MG_REQUIRE(!capturing, "checksum inside a captured cycle");
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(d_norm);
+    unsigned long long* h = reinterpret_cast<unsigned long long*>(h_norm);
+    MG_CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), stream));
+    const char* base = which_ptr(lv, w);
+    if (f64()) launch_checksum<double>(stream, lc, (const double*)base, lv.pitch, lv.N, lv.own_lo, lv.own_hi, d);
+    else launch_checksum<float>(stream, lc, (const float*)base, lv.pitch, lv.N, lv.own_lo, lv.own_hi, d);
+    MG_CK(cudaGetLastError());
+    MG_CK(cudaMemcpyAsync(h, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    MG_CK(cudaStreamSynchronize(stream));
+    return *h;
 }
 
 // ---------------------------------------------------------------------------------
@@ -551,9 +606,7 @@ float Ctx::time_op(int op, int level, int reps)
 {
     MG_REQUIRE(reps >= 1, "reps >= 1 required");
     L(level);
-    cudaEvent_t e0, e1;
-    MG_CK(cudaEventCreate(&e0));
-    MG_CK(cudaEventCreate(&e1));
+    EventTimer timer(stream);
     auto run = [&]() {
         switch (op) {
             case MG_OP_SMOOTH1: smooth(level, 1); break;
@@ -585,15 +638,9 @@ float Ctx::time_op(int op, int level, int reps)
     };
     run();  // warm
     MG_CK(cudaStreamSynchronize(stream));
-    MG_CK(cudaEventRecord(e0, stream));
+    timer.start();
     for (int i = 0; i < reps; ++i) run();
-    MG_CK(cudaEventRecord(e1, stream));
-    MG_CK(cudaEventSynchronize(e1));
-    float ms = 0.f;
-    MG_CK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    return ms;
+    return timer.stop();
 }
 
 }  // namespace mgb

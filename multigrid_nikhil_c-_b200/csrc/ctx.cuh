@@ -38,6 +38,34 @@ struct MgError : std::runtime_error {
         if (!(cond)) throw ::mgb::MgError(MG_ERR_ARG, std::string(msg)); \
     } while (0)
 
+// a pair of CUDA events around a timed region on one stream; destroyed on every path, including exceptions
+struct EventTimer {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t stream;
+    explicit EventTimer(cudaStream_t s) : stream(s)
+    {
+        MG_CK(cudaEventCreate(&e0));
+        cudaError_t e = cudaEventCreate(&e1);
+        if (e != cudaSuccess) { cudaEventDestroy(e0); e0 = nullptr; MG_CK(e); }
+    }
+    ~EventTimer()
+    {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+    EventTimer(const EventTimer&) = delete;
+    EventTimer& operator=(const EventTimer&) = delete;
+    void start() { MG_CK(cudaEventRecord(e0, stream)); }
+    float stop()   // milliseconds since start(); waits for the region to finish
+    {
+        MG_CK(cudaEventRecord(e1, stream));
+        MG_CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        MG_CK(cudaEventElapsedTime(&ms, e0, e1));
+        return ms;
+    }
+};
+
 struct Comm;  // comm.cuh (row-slab halo exchange; null when world == 1)
 
 constexpr int kHaloRows = 6;  // halo rows stored per side on distributed levels (deepest fused kernel: RB-GS PRE, NS=4)
@@ -59,13 +87,23 @@ struct Level {
     // number of valid halo rows (distributed levels) of the current u, of f and of r;
     // an operator that rewrites only the owned rows sets it to 0, Ctx::ensure_halo exchanges lazily
     int hv_u = 0, hv_f = 0, hv_r = 0;
-    // MGB200_ZERO_GUESS: the current u is LOGICALLY zero but its buffer was not written (the next kernel is a
+    // zero-guess chain: the current u is LOGICALLY zero but its buffer was not written (the next kernel is a
     // zero-guess variant that does not read it); Ctx::materialize_u writes the zeros for every other reader
     bool u_zero = false;
-    // MGB200_CHAIN, fullmultigrid: the current u is LOGICALLY the bare interpolation of the coarser level's iterate
+    // visit chains, fullmultigrid: the current u is LOGICALLY the bare interpolation of the coarser level's iterate
     // (P:645) but was not computed: the first PRE of the level does it on the fly (k_stream_fmg_entry);
     // Ctx::materialize_u runs the real prolongation for every other reader
     bool u_interp = false;
+};
+
+// per-context tuning state of the streaming kernels (fused.cu).  Per context, not per process: two contexts on two
+// devices of one process must not share the SM count or the knobs read at creation.
+struct FusedKnobs {
+    int num_sms = 148;
+    int occ = 12;              // resident streaming warps per SM (MGB200_STREAM_OCC), enforced by padding dynamic smem
+    bool autotune = true;      // MGB200_AUTOTUNE=0 disables the chunk-height tuner
+    int force_ry = 0;          // MGB200_STREAM_RY / _MINN: force the chunk height on levels with N >= minN (tuning sweeps)
+    int force_ry_minN = 4096;
 };
 
 struct GraphEntry {
@@ -91,19 +129,21 @@ struct Ctx {
     bool capturing = false;
     std::map<std::tuple<int, int, int, int, std::string>, GraphEntry> graphs;
     std::map<std::tuple<int, int, int, int>, int> stream_ry;  // tuned chunk height per (level, mode, NS, rbgs)
-    std::map<std::tuple<int, int, int, int>, std::pair<void*, int>> ctail_ops;  // cluster-tail op lists on the device
+    FusedKnobs knobs;
     Comm* comm = nullptr;
     int aggl_level = 0;  // levels <= aggl_level are replicated on every rank
     bool graph_dist = false;  // capture NCCL exchanges into cycle graphs (MGB200_GRAPH_DIST=1)
-    bool zero_guess = false;  // skip reading / writing the zero coarse guess (MGB200_ZERO_GUESS=1)
+    bool zero_guess = true;   // skip reading / writing the zero coarse guess (P:613) where the next kernel does not need it (MGB200_ZERO_GUESS=0 turns it off)
     bool comm_avoid = false;  // communication-avoiding slab schedule (MGB200_COMM_AVOID=1, csrc/sched.h)
     bool overlap = false;     // halo exchange on a second stream, overlapped with the interior rows (MGB200_OVERLAP=1)
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool chain = false;       // fuse POST of one visit of a level with PRE of the next (MGB200_CHAIN=1, stream.cuh MODE_POSTPRE)
+    bool chain = true;        // fuse POST of one visit of a level with PRE of the next (stream.cuh MODE_POSTPRE; MGB200_CHAIN=0 turns it off)
 
     explicit Ctx(const mg_config& c);
     ~Ctx();
+    void init();               // body of the constructor
+    void release() noexcept;   // frees everything (destructor, and the constructor's error path)
 
     Level& L(int level);
     const Level& L(int level) const;
@@ -115,6 +155,8 @@ struct Ctx {
     void get_host(int level, Which w, void* host);
     void zero_u(int level);
     void force_constant(double f);
+    void force_synthetic(unsigned long long seed);          // b = h^2 (2U-1), U from splitmix64(seed, global index)
+    unsigned long long checksum(int level, Which w);        // order-independent checksum of this rank's owned rows
 
     // operators
     void smooth(int level, int nu);

@@ -12,23 +12,8 @@
 #include "sched.h"
 #include "stream.cuh"
 #include "tail.cuh"
-#include "tile.cuh"
-#include "ctail.cuh"
 
 namespace mgb {
-
-static int g_num_sms = 148;
-static int g_force_ry = 0;
-static int g_force_ry_minN = 4096;
-static bool g_ctail = false;     // MGB200_CTAIL=1: cluster coarse tail for levels <= 8 (experimental, see ctail.cuh)
-static int g_ctail_ctas = 16;    // MGB200_CTAIL_CTAS: cluster size (power of two <= 16; > 8 is a non-portable cluster size)
-static bool g_tile = false;      // MGB200_TILE=1: shared-memory tile kernels on the mid levels (experimental, see tile.cuh)
-static int g_tile_maxN = 1024;
-static bool g_autotune = true;   // MGB200_AUTOTUNE=0 disables the chunk-height tuner
-static bool g_tma = false;       // MGB200_TMA=1: streaming kernels prefetch with bulk copies + mbarriers (experimental, stream.cuh)
-static int g_occ = 12;  // resident streaming warps per SM (MGB200_STREAM_OCC), enforced by padding dynamic shared memory
-
-void fused_setup_optin(Ctx& ctx);   // attributes of the opt-in kernels (defined below, next to them)
 
 template <typename T, int NS, int MODE, bool RBGS>
 static void set_attr()
@@ -59,41 +44,59 @@ static void set_attrs_t()
     MG_CK(cudaFuncSetAttribute(k_tail<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem_bytes<T>(kTailMaxLevel, 1)));
 }
 
+template <typename T>
+static void set_attrs_chain()
+{
+    const int big = 100 * 1024;
+    MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MG_CK(cudaFuncSetAttribute(k_stream_fmg_entry<T, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MG_CK(cudaFuncSetAttribute(k_stream_fmg_entry<T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MG_CK(cudaFuncSetAttribute(k_stream_fmg_entry<T, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MG_CK(cudaFuncSetAttribute(k_stream_fmg_entry<T, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MG_CK(cudaFuncSetAttribute(k_stream_pre_zg<T, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MG_CK(cudaFuncSetAttribute(k_stream_pre_zg<T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MG_CK(cudaFuncSetAttribute(k_stream_pre_zg<T, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MG_CK(cudaFuncSetAttribute(k_stream_pre_zg<T, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    const int ts = (int)tail_smem_bytes<T>(kTailMaxLevel, 1);
+    MG_CK(cudaFuncSetAttribute(k_tail_zg<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts));
+    MG_CK(cudaFuncSetAttribute(k_tail_zg<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts));
+}
+
+// Per CONTEXT, on the context's device (function attributes are per device; a second context on another device of the
+// same process gets its own), outside any stream capture.  Run-time knobs are read afresh for every context.
 void fused_setup(Ctx& ctx)
 {
     cudaDeviceProp prop;
     MG_CK(cudaGetDeviceProperties(&prop, ctx.device));
-    g_num_sms = prop.multiProcessorCount;
-    // run-time knobs: read afresh for every context (absent variable = default, so a knob never sticks in a process)
+    FusedKnobs& k = ctx.knobs;
+    k.num_sms = prop.multiProcessorCount;
     auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
-    g_force_ry = env_int("MGB200_STREAM_RY", 0);
-    g_force_ry_minN = env_int("MGB200_STREAM_RY_MINN", 4096);
-    g_occ = std::max(1, env_int("MGB200_STREAM_OCC", 12));
-    g_autotune = env_int("MGB200_AUTOTUNE", 1) != 0;
-    g_tile = env_int("MGB200_TILE", 0) != 0;
-    g_tile_maxN = env_int("MGB200_TILE_MAXN", 1024);
-    g_tma = env_int("MGB200_TMA", 0) != 0;
-    g_ctail = env_int("MGB200_CTAIL", 0) != 0;
-    g_ctail_ctas = std::max(1, std::min(kCtailMaxCtas, env_int("MGB200_CTAIL_CTAS", 16)));
-    if (ctx.f64()) set_attrs_t<double>();
-    else set_attrs_t<float>();
-    fused_setup_optin(ctx);
+    k.force_ry = env_int("MGB200_STREAM_RY", 0);
+    k.force_ry_minN = env_int("MGB200_STREAM_RY_MINN", 4096);
+    k.occ = std::max(1, env_int("MGB200_STREAM_OCC", 12));
+    k.autotune = env_int("MGB200_AUTOTUNE", 1) != 0;
+    if (ctx.f64()) { set_attrs_t<double>(); set_attrs_chain<double>(); }
+    else { set_attrs_t<float>(); set_attrs_chain<float>(); }
 }
 
 // ---------------------------------------------------------------------------------
 // one launch of a streaming kernel on level lv (lcv = next coarser level for PRE/POST)
 // ---------------------------------------------------------------------------------
 template <typename T, int NS, int MODE>
-static int default_ry(const Level& lv, int strips)
+static int default_ry(const Ctx& ctx, const Level& lv, int strips)
 {
-    // One wave of g_occ warps per SM: a partial last wave costs a whole chunk time, so the chunk height is
+    // One wave of knobs.occ warps per SM: a partial last wave costs a whole chunk time, so the chunk height is
     // chosen to make strips x chunks land on one wave whenever that keeps chunks <= 256 rows.
+    const FusedKnobs& kn = ctx.knobs;
     const int rows = lv.own_hi - lv.own_lo;
-    const int wave = g_num_sms * g_occ;
+    const int wave = kn.num_sms * kn.occ;
     const int chunks = std::max(1, wave / strips);
     int ry = (rows + chunks - 1) / chunks;
     ry = std::max(8, std::min(256, ry));
-    if (g_force_ry > 0 && lv.N >= g_force_ry_minN) ry = g_force_ry;   // MGB200_STREAM_RY[_MINN]: tuning knobs
+    if (kn.force_ry > 0 && lv.N >= kn.force_ry_minN) ry = kn.force_ry;   // MGB200_STREAM_RY[_MINN]: tuning knobs
     return (ry + 1) & ~1;
 }
 
@@ -114,7 +117,7 @@ static StreamArgs<T> make_args(Ctx& ctx, Level& lv, Level* lcv, int ry, int ya =
     const int rows = a.yb - a.ya;
     a.strips = std::max(1, (int)cdiv(std::max(1, lv.N - C::V * C::HLANES), C::OUTW));
     a.strips_pad = (a.strips + kStreamWarps - 1) / kStreamWarps * kStreamWarps;
-    if (ry <= 0) ry = default_ry<T, NS, MODE>(lv, a.strips);
+    if (ry <= 0) ry = default_ry<T, NS, MODE>(ctx, lv, a.strips);
     a.ry = ry;
     a.nitems = a.strips_pad * ((rows + ry - 1) / ry);
     const T om = (T)ctx.cfg.omega;
@@ -152,19 +155,22 @@ static StreamArgs<T> make_args(Ctx& ctx, Level& lv, Level* lcv, int ry, int ya =
     return a;
 }
 
+// dynamic shared memory of a streaming launch: the ring, padded so that at most knobs.occ warps are resident per SM
+template <typename C>
+static size_t stream_smem(const Ctx& ctx)
+{
+    return std::min<size_t>(100 * 1024, std::max<size_t>(C::SMEM_BYTES, (size_t)(227 * 1024) / std::max(1, ctx.knobs.occ / kStreamWarps) - 1024));
+}
+
 template <typename T, int NS, int MODE, bool RBGS>
 static void raw_launch(Ctx& ctx, const StreamArgs<T>& a)
 {
     typedef StreamCfg<T, NS, MODE> C;
     if (a.yb <= a.ya) return;
     const unsigned grid = cdiv(a.nitems, kStreamWarps);
-    // cap the resident warps per SM at g_occ by padding the dynamic shared memory
-    const size_t smem = std::min<size_t>(100 * 1024, std::max<size_t>(C::SMEM_BYTES, (size_t)(227 * 1024) / std::max(1, g_occ / kStreamWarps) - 1024));
+    const size_t smem = stream_smem<C>(ctx);
     if constexpr (MODE == MODE_POSTPRE) {
         k_stream_chain<T, NS, RBGS><<<grid, kStreamWarps * 32, smem, ctx.stream>>>(a);
-    } else if (g_tma) {
-        const size_t smem_tma = std::max<size_t>(smem, C::SMEM_BYTES + kStreamTmaExtraSmem);
-        k_stream_tma<T, NS, MODE, RBGS><<<grid, kStreamWarps * 32, smem_tma, ctx.stream>>>(a);
     } else {
         k_stream<T, NS, MODE, RBGS><<<grid, kStreamWarps * 32, smem, ctx.stream>>>(a);
     }
@@ -186,7 +192,7 @@ static int tuned_ry(Ctx& ctx, Level& lv, Level* lcv)
     auto it = ctx.stream_ry.find(key);
     if (it != ctx.stream_ry.end()) return it->second;
     StreamArgs<T> a0 = make_args<T, NS, MODE>(ctx, lv, lcv, 0);
-    if (lv.N < kTuneMinN || ctx.capturing || !g_autotune || g_force_ry > 0) return a0.ry;
+    if (lv.N < kTuneMinN || ctx.capturing || !ctx.knobs.autotune || ctx.knobs.force_ry > 0) return a0.ry;
     const int rows = lv.own_hi - lv.own_lo;
     std::vector<int> cand;
     auto add = [&](int ry) {
@@ -195,29 +201,23 @@ static int tuned_ry(Ctx& ctx, Level& lv, Level* lcv)
     };
     add(a0.ry);
     for (int w : {8, 10, 12, 16}) {
-        const int chunks = std::max(1, g_num_sms * w / a0.strips);
+        const int chunks = std::max(1, ctx.knobs.num_sms * w / a0.strips);
         const int ry = (rows + chunks - 1) / chunks;
         if (ry <= 512) add(ry);
     }
     add(128); add(192); add(256);
-    cudaEvent_t e0, e1;
-    MG_CK(cudaEventCreate(&e0));
-    MG_CK(cudaEventCreate(&e1));
+    EventTimer timer(ctx.stream);
     float best = 1e30f;
     int best_ry = a0.ry;
     for (int ry : cand) {
-        StreamArgs<T> a = make_args<T, NS, MODE>(ctx, lv, lcv, ry);
+        // no zero-guess store: lcv->u[0] may hold a coarse solution that fullmultigrid is about to interpolate (P:645)
+        StreamArgs<T> a = make_args<T, NS, MODE>(ctx, lv, lcv, ry, -1, -1, false);
         raw_launch<T, NS, MODE, RBGS>(ctx, a);   // warm-up
-        MG_CK(cudaEventRecord(e0, ctx.stream));
+        timer.start();
         for (int rep = 0; rep < kTuneReps; ++rep) raw_launch<T, NS, MODE, RBGS>(ctx, a);
-        MG_CK(cudaEventRecord(e1, ctx.stream));
-        MG_CK(cudaEventSynchronize(e1));
-        float ms = 0.f;
-        MG_CK(cudaEventElapsedTime(&ms, e0, e1));
+        const float ms = timer.stop();
         if (ms < best) { best = ms; best_ry = ry; }
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     ctx.lc.n -= (1 + kTuneReps) * (long long)cand.size();   // tuning launches are not part of the work
     ctx.stream_ry[key] = best_ry;
     return best_ry;
@@ -281,82 +281,6 @@ static void launch_stream(Ctx& ctx, Level& lv, Level* lcv)
     }
 }
 
-// ---------------------------------------------------------------------------------
-// shared-memory tile kernels for the mid levels (tile_core.h); same contract as launch_stream
-// ---------------------------------------------------------------------------------
-template <typename T, int NS, int MODE, bool RBGS, int TY, int TX>
-static void launch_tile_cfg(Ctx& ctx, Level& lv, Level* lcv)
-{
-    typedef TileCfg<T, NS, MODE, TY, TX> C;
-    static bool attr_set = false;
-    const size_t smem = (size_t)C::SMEM_ELEMS * sizeof(T);
-    if (!attr_set) {
-        MG_CK(cudaFuncSetAttribute(k_tile<T, NS, MODE, RBGS, TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    TileArgs<T> a;
-    a.u_in = (const T*)lv.u[lv.cur];
-    a.u_out = (T*)lv.u[lv.cur ^ 1];
-    a.f = (const T*)lv.f;
-    a.pitch = lv.pitch;
-    a.N = lv.N;
-    a.ya = lv.own_lo;
-    a.yb = lv.own_hi;
-    a.row_lo = lv.st_lo;
-    a.row_hi = lv.st_hi;
-    const T om = (T)ctx.cfg.omega;
-    a.c0 = (T)(1.0 - (double)om);
-    a.c1 = (T)((double)om / 4.0);
-    a.w = (T)ctx.cfg.restrict_weight;
-    a.fc = nullptr; a.uc = nullptr; a.ec = nullptr; a.pitch_c = 0; a.Nc = 0; a.crow_lo = a.crow_hi = 0;
-    if (MODE == TILE_PRE) {
-        a.fc = (T*)lcv->f;
-        a.uc = (lv.distributed && !lcv->distributed) ? nullptr : (T*)lcv->u[0];
-        a.pitch_c = lcv->pitch;
-        a.Nc = lcv->N;
-    } else if (MODE == TILE_POST) {
-        a.ec = (const T*)lcv->u[lcv->cur];
-        a.pitch_c = lcv->pitch;
-        a.Nc = lcv->N;
-        a.crow_lo = lcv->st_lo;
-        a.crow_hi = lcv->st_hi;
-    }
-    if (a.yb <= a.ya) return;
-    dim3 grid(cdiv(lv.N, TX), cdiv(a.yb - a.ya, TY));
-    k_tile<T, NS, MODE, RBGS, TY, TX><<<grid, kTileThreads, smem, ctx.stream>>>(a);
-    ++ctx.lc.n;
-    MG_CK(cudaGetLastError());
-}
-
-template <typename T, int NS, int MODE, bool RBGS>
-static void launch_tile(Ctx& ctx, Level& lv, Level* lcv)
-{
-    ctx.materialize_u(lv);
-    if (MODE == TILE_POST) ctx.materialize_u(*lcv);
-    // same halo contract as the streaming kernels (MODE values coincide)
-    ctx.ensure_halo(lv, Ctx::W_U, NS + (MODE == TILE_PRE ? 2 : 0));
-    ctx.ensure_halo(lv, Ctx::W_F, NS + (MODE == TILE_PRE ? 1 : 0) - (MODE == TILE_SWEEPS ? 1 : 0));
-    if (MODE == TILE_PRE) lcv->cur = 0;
-    if (MODE == TILE_POST) ctx.ensure_halo(*lcv, Ctx::W_U, NS / 2 + 1);
-    if (lv.N <= 256) launch_tile_cfg<T, NS, MODE, RBGS, 16, 32>(ctx, lv, lcv);
-    else launch_tile_cfg<T, NS, MODE, RBGS, 32, 64>(ctx, lv, lcv);
-    lv.cur ^= 1;
-    lv.hv_u = 0;
-    if (MODE == TILE_PRE) {
-        lcv->u_zero = false;
-        if (lv.distributed && !lcv->distributed) {
-            comm_allgather_rows(ctx, *lcv, lcv->f);
-            MG_CK(cudaMemsetAsync(lcv->alloc[0], 0, lcv->bytes, ctx.stream));
-        } else if (lcv->distributed) {
-            lcv->hv_f = 0;
-            comm_zero_halo(ctx, *lcv, lcv->u[0]);
-            lcv->hv_u = lcv->halo;
-        }
-    }
-}
-
-static bool use_tile(const Level& lv) { return g_tile && lv.N <= g_tile_maxN; }
-
 static bool stream_ok(const Ctx& ctx, const Level&)
 {
     return (ctx.cfg.flags & MG_FUSED) != 0;
@@ -382,7 +306,6 @@ template int fused_jacobi<float>(Ctx&, Level&, int, float, float);
 // iterate goes through Ctx::materialize_u, so a wrong prediction costs time, never correctness.
 // ---------------------------------------------------------------------------------
 static int tail_top(const Ctx& ctx);
-static bool use_tile(const Level& lv);
 
 static bool child_takes_zero_guess(Ctx& ctx, Level& lv, int nu1)
 {
@@ -391,7 +314,7 @@ static bool child_takes_zero_guess(Ctx& ctx, Level& lv, int nu1)
     if (c < ctx.cfg.coarsest_level || ctx.L(c).distributed) return false;
     if (c == tail_top(ctx)) return true;
     if (c <= ctx.cfg.coarsest_level) return false;
-    return nu1 >= 1 && nu1 <= 2 && !use_tile(ctx.L(c));
+    return nu1 >= 1 && nu1 <= 2;
 }
 
 template <typename T, int NS, bool RBGS>
@@ -404,12 +327,7 @@ static void launch_pre_zero_guess(Ctx& ctx, Level& lv, Level* lcv, bool write_ze
     const StreamArgs<T> a = make_args<T, NS, MODE_PRE>(ctx, lv, lcv, ry, -1, -1, write_zero_guess);
     if (a.yb > a.ya) {
         typedef StreamCfg<T, NS, MODE_PRE> C;
-        static bool attr_set = false;
-        if (!attr_set) {
-            MG_CK(cudaFuncSetAttribute(k_stream_pre_zg<T, NS, RBGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            attr_set = true;
-        }
-        const size_t smem = std::min<size_t>(100 * 1024, std::max<size_t>(C::SMEM_BYTES, (size_t)(227 * 1024) / std::max(1, g_occ / kStreamWarps) - 1024));
+        const size_t smem = stream_smem<C>(ctx);
         k_stream_pre_zg<T, NS, RBGS><<<cdiv(a.nitems, kStreamWarps), kStreamWarps * 32, smem, ctx.stream>>>(a);
         ++ctx.lc.n;
         MG_CK(cudaGetLastError());
@@ -443,7 +361,7 @@ static void pre_fused(Ctx& ctx, Level& lv, Level& lcv, int nu1)
         if (fmg_entry_fused<T>(ctx, lv, lcv, nu1)) return;
         ctx.materialize_u(lv);
     }
-    if (ctx.zero_guess && !use_tile(lv) && !lv.distributed) {
+    if (ctx.zero_guess && !lv.distributed) {
         // opt-in zero-guess chain
         const bool wz = !child_takes_zero_guess(ctx, lv, nu1);
         if (lv.u_zero && nu1 == k) {
@@ -486,16 +404,6 @@ static void pre_fused(Ctx& ctx, Level& lv, Level& lcv, int nu1)
         }
     }
     stream_sweeps<T>(ctx, lv, nu1 - k);
-    if (use_tile(lv)) {
-        if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) {
-            if (k == 2) launch_tile<T, 2, TILE_PRE, false>(ctx, lv, &lcv);
-            else launch_tile<T, 1, TILE_PRE, false>(ctx, lv, &lcv);
-        } else {
-            if (k == 2) launch_tile<T, 4, TILE_PRE, true>(ctx, lv, &lcv);
-            else launch_tile<T, 2, TILE_PRE, true>(ctx, lv, &lcv);
-        }
-        return;
-    }
     if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) {
         if (k == 2) launch_stream<T, 2, MODE_PRE, false>(ctx, lv, &lcv);
         else launch_stream<T, 1, MODE_PRE, false>(ctx, lv, &lcv);
@@ -509,17 +417,6 @@ template <typename T>
 static void post_fused(Ctx& ctx, Level& lv, Level& lcv, int nu2)
 {
     const int k = std::min(nu2, 2);
-    if (use_tile(lv)) {
-        if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) {
-            if (k == 2) launch_tile<T, 2, TILE_POST, false>(ctx, lv, &lcv);
-            else launch_tile<T, 1, TILE_POST, false>(ctx, lv, &lcv);
-        } else {
-            if (k == 2) launch_tile<T, 4, TILE_POST, true>(ctx, lv, &lcv);
-            else launch_tile<T, 2, TILE_POST, true>(ctx, lv, &lcv);
-        }
-        stream_sweeps<T>(ctx, lv, nu2 - k);
-        return;
-    }
     if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) {
         if (k == 2) launch_stream<T, 2, MODE_POST, false>(ctx, lv, &lcv);
         else launch_stream<T, 1, MODE_POST, false>(ctx, lv, &lcv);
@@ -538,7 +435,7 @@ static void post_fused(Ctx& ctx, Level& lv, Level& lcv, int nu2)
 // ---------------------------------------------------------------------------------
 static int postpre_ns(const Ctx& ctx, const Level& lv, int nu1, int nu2)
 {
-    if (!ctx.chain || !(ctx.cfg.flags & MG_FUSED) || use_tile(lv) || (lv.distributed && ctx.comm_avoid)) return 0;
+    if (!ctx.chain || !(ctx.cfg.flags & MG_FUSED) || (lv.distributed && ctx.comm_avoid)) return 0;
     if (nu1 < 1 || nu2 < 1 || nu1 > 2 || nu2 > 2) return 0;
     if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) return nu1 + nu2;          // 2, 3 or 4 pipeline stages
     return (nu1 == 1 && nu2 == 1) ? 4 : 0;                               // RB-GS: one stage per colour
@@ -547,13 +444,6 @@ static int postpre_ns(const Ctx& ctx, const Level& lv, int nu1, int nu2)
 template <typename T, int NS, bool RBGS>
 static void launch_postpre(Ctx& ctx, Level& lv, Level& lcv, bool write_zero_guess)
 {
-    typedef StreamCfg<T, NS, MODE_POSTPRE> C;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MG_CK(cudaFuncSetAttribute(k_stream_chain<T, NS, RBGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)std::max<size_t>(C::SMEM_BYTES, 100 * 1024)));
-        attr_set = true;
-    }
     ctx.materialize_u(lv);
     ctx.materialize_u(lcv);
     // row slabs: halo rows the pipeline reaches into (PRE's needs on u and f, POST's on the coarse correction)
@@ -602,16 +492,11 @@ template <typename T, int NS, bool RBGS>
 static void launch_fmg_entry(Ctx& ctx, Level& lv, Level& lcv, bool write_zero_guess)
 {
     typedef StreamCfg<T, NS, MODE_POSTPRE> C;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MG_CK(cudaFuncSetAttribute(k_stream_fmg_entry<T, NS, RBGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set = true;
-    }
     ctx.materialize_u(lcv);
     lv.u_interp = false;                       // consumed here: stage 0 of the kernel is P u_c
     StreamArgs<T> a = make_args<T, NS, MODE_POSTPRE>(ctx, lv, &lcv, 0, -1, -1, write_zero_guess);
     if (a.yb > a.ya) {
-        const size_t smem = std::min<size_t>(100 * 1024, std::max<size_t>(C::SMEM_BYTES, (size_t)(227 * 1024) / std::max(1, g_occ / kStreamWarps) - 1024));
+        const size_t smem = stream_smem<C>(ctx);
         k_stream_fmg_entry<T, NS, RBGS><<<cdiv(a.nitems, kStreamWarps), kStreamWarps * 32, smem, ctx.stream>>>(a);
         ++ctx.lc.n;
         MG_CK(cudaGetLastError());
@@ -629,7 +514,7 @@ static void launch_fmg_entry(Ctx& ctx, Level& lv, Level& lcv, bool write_zero_gu
 template <typename T>
 static bool fmg_entry_fused(Ctx& ctx, Level& lv, Level& lcv, int nu1)
 {
-    if (!ctx.chain || lv.distributed || use_tile(lv) || nu1 < 1 || nu1 > 2) return false;
+    if (!ctx.chain || lv.distributed || nu1 < 1 || nu1 > 2) return false;
     const bool wz = !child_takes_zero_guess(ctx, lv, nu1);
     if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) {
         if (nu1 == 2) launch_fmg_entry<T, 2, false>(ctx, lv, lcv, wz);
@@ -672,13 +557,7 @@ static void run_tail(Ctx& ctx, int level, int nu1, int nu2, int gamma)
     a.f = (const T*)lv.f;
     a.pitch = lv.pitch;
     const size_t smem = tail_smem_bytes<T>(level, a.coarsest);
-    if (lv.u_zero) {   // opt-in zero-guess chain: u is logically zero and is not read
-        static bool attr_set = false;
-        if (!attr_set) {
-            MG_CK(cudaFuncSetAttribute(k_tail_zg<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem_bytes<T>(kTailMaxLevel, 1)));
-            MG_CK(cudaFuncSetAttribute(k_tail_zg<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem_bytes<T>(kTailMaxLevel, 1)));
-            attr_set = true;
-        }
+    if (lv.u_zero) {   // zero-guess chain: u is logically zero and is not read
         if (ctx.cfg.smoother == MG_SMOOTH_RBGS) k_tail_zg<T, true><<<1, kTailThreads, smem, ctx.stream>>>(a);
         else k_tail_zg<T, false><<<1, kTailThreads, smem, ctx.stream>>>(a);
         lv.u_zero = false;
@@ -687,78 +566,6 @@ static void run_tail(Ctx& ctx, int level, int nu1, int nu2, int gamma)
     else k_tail<T, false><<<1, kTailThreads, smem, ctx.stream>>>(a);
     ++ctx.lc.n;
     MG_CK(cudaGetLastError());
-}
-
-// ---------------------------------------------------------------------------------
-// cluster coarse tail (ctail_core.h), opt-in MGB200_CTAIL=1: levels <= ctail_top in one cluster launch
-// ---------------------------------------------------------------------------------
-static int ctail_top(const Ctx& ctx)
-{
-    if (!g_ctail || (g_ctail_ctas & (g_ctail_ctas - 1))) return -1;
-    int top = std::min(kCtailMaxLevel, ctx.cfg.finest_level);
-    while (top >= ctx.cfg.coarsest_level) {
-        const size_t bytes = ctx.f64() ? ctail_smem_bytes<double>(top, g_ctail_ctas) : ctail_smem_bytes<float>(top, g_ctail_ctas);
-        if (bytes <= 227 * 1024) break;
-        --top;
-    }
-    if (top < ctx.cfg.coarsest_level || ctx.L(top).distributed) return -1;
-    return top;
-}
-
-// the op list of a cycle visit, uploaded once per (level, nu1, nu2, gamma); must exist before graph capture
-static const CtailOp* ctail_ops(Ctx& ctx, int level, int nu1, int nu2, int gamma, int* nops)
-{
-    const auto key = std::make_tuple(level, nu1, nu2, gamma);
-    auto it = ctx.ctail_ops.find(key);
-    if (it == ctx.ctail_ops.end()) {
-        if (ctx.capturing) throw MgError(MG_ERR_STATE, "cluster-tail schedule requested during graph capture");
-        const std::vector<CtailOp> ops = ctail_schedule(level, ctx.cfg.coarsest_level, nu1, nu2, gamma, ctx.cfg.smoother == MG_SMOOTH_RBGS);
-        void* d = nullptr;
-        MG_CK(cudaMalloc(&d, ops.size() * sizeof(CtailOp)));
-        MG_CK(cudaMemcpy(d, ops.data(), ops.size() * sizeof(CtailOp), cudaMemcpyHostToDevice));
-        it = ctx.ctail_ops.emplace(key, std::make_pair(d, (int)ops.size())).first;
-    }
-    *nops = it->second.second;
-    return (const CtailOp*)it->second.first;
-}
-
-template <typename T>
-static void run_ctail(Ctx& ctx, int level, int nu1, int nu2, int gamma)
-{
-    Level& lv = ctx.L(level);
-    ctx.materialize_u(lv);
-    CtailArgs<T> a;
-    a.top = level;
-    a.nctas = g_ctail_ctas;
-    a.ops = ctail_ops(ctx, level, nu1, nu2, gamma, &a.nops);
-    const T om = (T)ctx.cfg.omega;
-    a.c0 = (T)(1.0 - (double)om);
-    a.c1 = (T)((double)om / 4.0);
-    a.w = (T)ctx.cfg.restrict_weight;
-    a.u = (T*)lv.u[lv.cur];
-    a.f = (const T*)lv.f;
-    a.pitch = lv.pitch;
-    const size_t smem = ctail_smem_bytes<T>(level, g_ctail_ctas);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MG_CK(cudaFuncSetAttribute(k_ctail<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        MG_CK(cudaFuncSetAttribute(k_ctail<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        attr_set = true;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)g_ctail_ctas);
-    cfg.blockDim = dim3(kCtailThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = ctx.stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)g_ctail_ctas;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    MG_CK(cudaLaunchKernelEx(&cfg, k_ctail<T>, a));
-    ++ctx.lc.n;
 }
 
 // ---------------------------------------------------------------------------------
@@ -846,83 +653,9 @@ static bool comm_avoid_cycle(Ctx& ctx, int level, int nu1, int nu2, int gamma)
     return true;
 }
 
-// The opt-in kernels opt into large dynamic shared memory (and the cluster kernel into a non-portable cluster size).
-// Do that once per context, OUTSIDE any stream capture; the launch sites keep a lazy fallback.
-template <typename T, int NS, int MODE, bool RBGS>
-static void tile_attrs()
-{
-    MG_CK(cudaFuncSetAttribute(k_tile<T, NS, MODE, RBGS, 16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)((size_t)TileCfg<T, NS, MODE, 16, 32>::SMEM_ELEMS * sizeof(T))));
-    MG_CK(cudaFuncSetAttribute(k_tile<T, NS, MODE, RBGS, 32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)((size_t)TileCfg<T, NS, MODE, 32, 64>::SMEM_ELEMS * sizeof(T))));
-}
-
-template <typename T, int NS, int MODE, bool RBGS>
-static void tma_attr()
-{
-    MG_CK(cudaFuncSetAttribute(k_stream_tma<T, NS, MODE, RBGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-}
-
-template <typename T>
-static void optin_attrs(Ctx& ctx)
-{
-    const int big = 100 * 1024;
-    if (g_tma) {   // the same instantiations as set_attrs_t
-        tma_attr<T, 1, MODE_SWEEPS, false>(); tma_attr<T, 2, MODE_SWEEPS, false>(); tma_attr<T, 3, MODE_SWEEPS, false>();
-        tma_attr<T, 4, MODE_SWEEPS, false>(); tma_attr<T, 1, MODE_PRE, false>(); tma_attr<T, 2, MODE_PRE, false>();
-        tma_attr<T, 1, MODE_POST, false>(); tma_attr<T, 2, MODE_POST, false>(); tma_attr<T, 2, MODE_SWEEPS, true>();
-        tma_attr<T, 4, MODE_SWEEPS, true>(); tma_attr<T, 2, MODE_PRE, true>(); tma_attr<T, 4, MODE_PRE, true>();
-        tma_attr<T, 2, MODE_POST, true>(); tma_attr<T, 4, MODE_POST, true>();
-    }
-    if (ctx.chain) {
-        MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        MG_CK(cudaFuncSetAttribute(k_stream_fmg_entry<T, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        MG_CK(cudaFuncSetAttribute(k_stream_fmg_entry<T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        MG_CK(cudaFuncSetAttribute(k_stream_fmg_entry<T, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        MG_CK(cudaFuncSetAttribute(k_stream_fmg_entry<T, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    }
-    if (ctx.zero_guess) {
-        MG_CK(cudaFuncSetAttribute(k_stream_pre_zg<T, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        MG_CK(cudaFuncSetAttribute(k_stream_pre_zg<T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        MG_CK(cudaFuncSetAttribute(k_stream_pre_zg<T, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        MG_CK(cudaFuncSetAttribute(k_stream_pre_zg<T, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        const int ts = (int)tail_smem_bytes<T>(kTailMaxLevel, 1);
-        MG_CK(cudaFuncSetAttribute(k_tail_zg<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts));
-        MG_CK(cudaFuncSetAttribute(k_tail_zg<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts));
-    }
-    if (g_tile) {
-        tile_attrs<T, 1, TILE_PRE, false>();
-        tile_attrs<T, 2, TILE_PRE, false>();
-        tile_attrs<T, 1, TILE_POST, false>();
-        tile_attrs<T, 2, TILE_POST, false>();
-        tile_attrs<T, 2, TILE_PRE, true>();
-        tile_attrs<T, 4, TILE_PRE, true>();
-        tile_attrs<T, 2, TILE_POST, true>();
-        tile_attrs<T, 4, TILE_POST, true>();
-    }
-    if (g_ctail) {
-        MG_CK(cudaFuncSetAttribute(k_ctail<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        MG_CK(cudaFuncSetAttribute(k_ctail<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    }
-}
-
-void fused_setup_optin(Ctx& ctx)
-{
-    if (ctx.f64()) optin_attrs<double>(ctx);
-    else optin_attrs<float>(ctx);
-}
-
 bool fused_cycle_level(Ctx& ctx, int level, int nu1, int nu2, int gamma)
 {
     if (comm_avoid_cycle(ctx, level, nu1, nu2, gamma)) return true;
-    if (level == ctail_top(ctx)) {
-        if (ctx.f64()) run_ctail<double>(ctx, level, nu1, nu2, gamma);
-        else run_ctail<float>(ctx, level, nu1, nu2, gamma);
-        return true;
-    }
     if (level == tail_top(ctx)) {
         if (ctx.f64()) run_tail<double>(ctx, level, nu1, nu2, gamma);
         else run_tail<float>(ctx, level, nu1, nu2, gamma);
@@ -945,7 +678,7 @@ bool fused_cycle_level(Ctx& ctx, int level, int nu1, int nu2, int gamma)
 bool fused_cycle_chain(Ctx& ctx, int level, int nu1, int nu2, int gamma, int visits)
 {
     if (visits < 2 || level <= ctx.cfg.coarsest_level) return false;
-    if (level == ctail_top(ctx) || level == tail_top(ctx)) return false;   // one launch per visit already
+    if (level == tail_top(ctx)) return false;   // one launch per visit already
     Level& lv = ctx.L(level);
     Level& lcv = ctx.L(level - 1);
     const int ns = postpre_ns(ctx, lv, nu1, nu2);
@@ -998,10 +731,6 @@ static void pretune_t(Ctx& ctx, int level, int nu1, int nu2)
 
 void fused_pretune(Ctx& ctx, int level, int nu1, int nu2, int gamma)
 {
-    {   // the cluster tail's op list must be on the device before a graph is captured
-        const int ct = ctail_top(ctx);
-        if (ct >= 0 && ct <= level) { int n; ctail_ops(ctx, ct, nu1, nu2, gamma, &n); }
-    }
     if (!(ctx.cfg.flags & MG_FUSED) || nu1 < 1 || nu2 < 1) return;
     if (ctx.f64()) pretune_t<double>(ctx, level, nu1, nu2);
     else pretune_t<float>(ctx, level, nu1, nu2);

@@ -5,6 +5,8 @@
 // L1).  Algorithmic traffic: 3 S bytes per point for smoother and residual.
 #pragma once
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mgb {
@@ -304,6 +306,70 @@ k_fill(T* __restrict__ p, i64 pitch, int N, int ya, int yb, T value)
     stv<T>(p + (i64)y * pitch + c, o);
 }
 
+// ---------------------------------------------------------------------------------
+// Synthetic right-hand side for benchmarks (no reference counterpart: the reference only has the constant f = 4,
+// P:123): b(y, x) = h^2 * (2 U - 1), U = top 53 bits of splitmix64(seed, idx) * 2^-53, idx = the reference's interior
+// index (y-1)*n + (x-1) (P:227-228).  A pure function of the GLOBAL index, so every rank of a row-slab run -- and the
+// single-GPU run of the same grid -- holds the same values without any host-side generation or transfer.
+// ---------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long seed, unsigned long long idx)
+{
+    unsigned long long z = seed + (idx + 1ull) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_fill_synthetic(T* __restrict__ p, i64 pitch, int N, int ya, int yb, double h2, unsigned long long seed)
+{
+    constexpr int V = Vec<T>::N;
+    const int c = V * (blockIdx.x * 256 + threadIdx.x);
+    const int y = ya + blockIdx.y;
+    if (c >= N || y >= yb) return;
+    const unsigned long long n = (unsigned long long)(N - 1);
+    T o[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int x = c + k;
+        if (x >= 1 && x < N) {
+            const unsigned long long z = splitmix64(seed, (unsigned long long)(y - 1) * n + (unsigned long long)(x - 1));
+            const double u01 = (double)(z >> 11) * 0x1.0p-53;      // exact
+            o[k] = (T)(h2 * (2.0 * u01 - 1.0));                    // exact in fp64 (h2 is a power of two); one rounding in fp32
+        } else {
+            o[k] = (T)0;
+        }
+    }
+    stv<T>(p + (i64)y * pitch + c, o);
+}
+
+// ---------------------------------------------------------------------------------
+// Order-independent 64-bit checksum of the interior values of rows [ya, yb): the sum (mod 2^64) over the points of
+// splitmix64(value bits, global interior index).  Integer addition is associative, so the checksum of a grid is the sum
+// of the checksums of its row slabs: N ranks and one rank agree exactly when every owned value agrees bit for bit.
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_checksum(const T* __restrict__ p, i64 pitch, int N, int ya, int yb, unsigned long long* __restrict__ out)
+{
+    const int x = blockIdx.x * 256 + threadIdx.x + 1;
+    unsigned long long acc = 0;
+    if (x < N) {
+        const unsigned long long n = (unsigned long long)(N - 1);
+        for (int y = ya + blockIdx.y; y < yb; y += gridDim.y) {
+            const T v = p[(i64)y * pitch + x];
+            unsigned long long bits;
+            if constexpr (sizeof(T) == 8) bits = (unsigned long long)__double_as_longlong(v);
+            else bits = (unsigned long long)__float_as_uint(v);
+            acc += splitmix64(bits, (unsigned long long)(y - 1) * n + (unsigned long long)(x - 1));
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, s);
+    if ((threadIdx.x & 31) == 0 && acc != 0) atomicAdd(out, acc);
+}
+
 // pack / unpack between the reference's interior-only host layout (staged flat in device
 // memory, n x n row-major) and the padded device layout.  Rows [ya, yb) (node rows).
 template <typename T, bool TO_PADDED>
@@ -403,6 +469,26 @@ inline void launch_fill(cudaStream_t st, LaunchCounter& lc, T* p, i64 pitch, int
     if (ya >= yb) return;
     dim3 grid(cdiv(N, Vec<T>::N * 256), (unsigned)(yb - ya));
     k_fill<T><<<grid, 256, 0, st>>>(p, pitch, N, ya, yb, value);
+    ++lc.n;
+}
+
+template <typename T>
+inline void launch_fill_synthetic(cudaStream_t st, LaunchCounter& lc, T* p, i64 pitch, int N, int ya, int yb, double h2,
+                                  unsigned long long seed)
+{
+    if (ya >= yb) return;
+    dim3 grid(cdiv(N, Vec<T>::N * 256), (unsigned)(yb - ya));
+    k_fill_synthetic<T><<<grid, 256, 0, st>>>(p, pitch, N, ya, yb, h2, seed);
+    ++lc.n;
+}
+
+template <typename T>
+inline void launch_checksum(cudaStream_t st, LaunchCounter& lc, const T* p, i64 pitch, int N, int ya, int yb,
+                            unsigned long long* out)
+{
+    if (ya >= yb || N < 2) return;
+    dim3 grid(cdiv(N - 1, 256), (unsigned)std::min(yb - ya, 64));
+    k_checksum<T><<<grid, 256, 0, st>>>(p, pitch, N, ya, yb, out);
     ++lc.n;
 }
 

@@ -119,45 +119,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 #endif
 
-// ---- TMA path (opt-in MGB200_TMA=1): 1-D bulk copies global -> shared (cp.async.bulk, SASS UBLKCP) completing on an
-//      mbarrier per ring slot, issued by ONE lane per row instead of a 16-byte cp.async by every lane ----
-#ifdef MGB_EMU
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)(uintptr_t)p; }
-__device__ __forceinline__ void mbar_init(void*, unsigned) {}
-__device__ __forceinline__ void mbar_init_fence() {}
-__device__ __forceinline__ void mbar_expect_tx(void*, unsigned) {}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, void*) { memcpy(dst, src, bytes); }
-__device__ __forceinline__ void mbar_wait(void*, unsigned) {}
-__device__ __forceinline__ void fence_proxy_async() {}
-#else
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(void* mb, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(mb)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(void* mb, unsigned tx)
-{
-    asm volatile("mbarrier.arrive.expect_tx.relaxed.cta.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(mb)), "r"(tx) : "memory");
-}
-// size and both addresses are multiples of 16 bytes (host-checked geometry: pitch % 32 == 0, strip offsets % 8 == 0)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, void* mb)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(mb)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(void* mb, unsigned parity)
-{
-    asm volatile("{\n\t.reg .pred p;\nMBW_TRY:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra MBW_DONE;\n\tbra MBW_TRY;\nMBW_DONE:\n}\n"
-                 ::"r"(smem_u32(mb)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-#endif
-
 // ZG ("zero guess"): the input iterate is known to be identically zero (first visit of a coarse level, P:613):
 // u is neither prefetched nor read, stage 0 is the constant 0.  Same arithmetic on the same values => same bits.
-// TMA: the prefetch uses bulk copies + mbarriers (above) instead of per-lane cp.async; everything else is unchanged.
-template <typename T, int NS, int MODE, bool RBGS, bool ZG = false, bool TMA = false>
+template <typename T, int NS, int MODE, bool RBGS, bool ZG = false>
 struct Streamer {
     typedef StreamCfg<T, NS, MODE> C;
     static constexpr int V = C::V;
@@ -183,13 +147,6 @@ struct Streamer {
     const T* safe_u;  // mapped addresses handed to ignored copies
     const T* safe_f;
     const T* safe_c;
-    // TMA path
-    unsigned long long* mbar;   // this warp's kRingSlots mbarriers (one per ring slot)
-    int it;                     // outer iteration (ring block) counter: slot set = it & 3, phase parity = (it >> 2) & 1
-    int lane_id, y_last;        // rows beyond y_last are never consumed and are not fetched
-    unsigned bytes_u, bytes_c;  // bytes of one row segment of this strip that exist in memory (the rest of a slot stays zero)
-    bool dead_;
-
     T W[C::NW > 0 ? C::NW : 1][3][V];
     T WL[C::NW > 0 ? C::NW : 1][3], WR[C::NW > 0 ? C::NW : 1][3];
     T R[3][V], RL[3];  // PRE: residual window (left neighbours only)
@@ -220,44 +177,6 @@ struct Streamer {
     {
         constexpr int b = REL / 3, s = REL % 3;
         T* dst = blk[b & 3] + s * C::SLOT_ELEMS;
-        if constexpr (TMA) {
-            // warp-uniform validity of the whole row; lanes whose columns lie beyond the pitch keep the zeros of the
-            // initial fill (a bulk copy writes only the bytes_u bytes that exist)
-            const bool rv = !dead_ && (y >= a.row_lo) && (y < a.row_hi) && (y <= y_last);
-            bool cv = false;
-            T* cdst = nullptr;
-            if (C::HAS_POST) {
-                const int ic = (y + 1) >> 1;
-                cv = !dead_ && (ic >= a.crow_lo) && (ic < a.crow_hi) && (y >= 0) && (y <= y_last) && bytes_c > 0;
-                cdst = cblk[b & 3] + s * C::CSLOT_ELEMS;
-            }
-            if (!rv) {   // row outside the grid / the slab: zeros, written by every lane for its own 16 bytes
-                T z[V];
-#pragma unroll
-                for (int k = 0; k < V; ++k) z[k] = (T)0;
-                if (!ZG) stv<T>(dst, z);
-                stv<T>(dst + 32 * V, z);
-            }
-            if (C::HAS_POST && !cv) {
-#pragma unroll
-                for (int k = 0; k < H; ++k) cdst[k] = (T)0;
-            }
-            if (!rv || (C::HAS_POST && !cv)) fence_proxy_async();   // generic writes before later bulk writes to the slot
-            if (lane_id == 0) {
-                void* mb = mbar + (((it + b) & 3) * 3 + s);
-                const unsigned tx = (rv ? (ZG ? 1u : 2u) * bytes_u : 0u) + (cv ? bytes_c : 0u);
-                mbar_expect_tx(mb, tx);
-                if (rv) {
-                    if (!ZG) bulk_g2s(dst, g_u, bytes_u, mb);
-                    bulk_g2s(dst + 32 * V, g_f, bytes_u, mb);
-                }
-                if (cv) bulk_g2s(cdst, g_c, bytes_c, mb);
-            }
-            g_u += a.pitch;
-            g_f += a.pitch;
-            if (C::HAS_POST && !(y & 1)) g_c += a.pitch_c;
-            return;
-        }
         const bool v = lane_ld && (y >= a.row_lo) && (y < a.row_hi);
         if (!ZG) cp_async16(dst, v ? g_u : safe_u, v);
         cp_async16(dst + 32 * V, v ? g_f : safe_f, v);
@@ -273,14 +192,23 @@ struct Streamer {
         cp_async_commit();
     }
 
+    // `need` (warp-uniform): bit 0 = the consumer of this row reads the left neighbour lane's last value, bit 1 = the
+    // right neighbour lane's first value.  Jacobi and the residual need both; a red-black stage needs exactly one (below).
     template <int NEW>
-    __device__ __forceinline__ void put_row(int s, const T (&v)[V])
+    __device__ __forceinline__ void put_row(int s, const T (&v)[V], int need = 3)
     {
 #pragma unroll
         for (int k = 0; k < V; ++k) W[s][NEW][k] = v[k];
-        WL[s][NEW] = __shfl_up_sync(FULL, v[V - 1], 1);
-        WR[s][NEW] = __shfl_down_sync(FULL, v[0], 1);
+        if (need & 1) WL[s][NEW] = __shfl_up_sync(FULL, v[V - 1], 1);
+        if (need & 2) WR[s][NEW] = __shfl_down_sync(FULL, v[0], 1);
     }
+
+    // Red-black Gauss-Seidel: stage t (1-based) updates colour (t-1)&1 on row `row`.  Every lane's first column c is even
+    // (strip origins and lane offsets are multiples of V), so the columns of that colour are the k with k % 2 == kk,
+    // kk = (row + colour) & 1 -- the same for the whole warp.  A stage therefore computes V/2 points per lane, not V,
+    // and needs only ONE neighbour-lane value: the left one when kk == 0 (k = 0 is updated), the right one when kk == 1.
+    static __device__ __forceinline__ int rb_kk(int row, int t) { return (row + ((t - 1) & 1)) & 1; }
+    static __device__ __forceinline__ int rb_need(int row, int t) { return rb_kk(row, t) ? 2 : 1; }
 
     // Dirichlet ring: only rows 0 / N (rows beyond them are zero by construction) and, on
     // strips touching the boundary, the columns flagged in cz[] ever need forcing.
@@ -294,6 +222,11 @@ struct Streamer {
             if constexpr (sizeof(T) == 8) o[k] = __longlong_as_double((long long)((unsigned long long)__double_as_longlong(o[k]) & cm[k]));
             else o[k] = __uint_as_float(__float_as_uint(o[k]) & cm[k]);
         }
+    }
+    __device__ __forceinline__ void mask_col(T& o, int k) const
+    {
+        if constexpr (sizeof(T) == 8) o = __longlong_as_double((long long)((unsigned long long)__double_as_longlong(o) & cm[k]));
+        else o = __uint_as_float(__float_as_uint(o) & cm[k]);
     }
     __device__ __forceinline__ bool ring_row(int row) const { return (row <= 0) || (row >= a.N); }
 
@@ -337,7 +270,7 @@ struct Streamer {
             for (int k = 0; k < V; ++k) cur[k] = ring_row(y) ? (T)0 : (ZG ? e[k] : cur[k] + e[k]);   // P:623 (ZG: bare interpolation, P:645)
             mask_cols(cur);
         }
-        put_row<NEW>(0, cur);
+        put_row<NEW>(0, cur, (RBGS && NS >= 1) ? rb_need(y, 1) : 3);
 
         // ---- smoothing stages: stage s produces row y-s of u_s from the window of u_{s-1} ----
 #pragma unroll
@@ -351,22 +284,34 @@ struct Streamer {
             if (ring_row(rs)) {   // warp-uniform, rare
 #pragma unroll
                 for (int k = 0; k < V; ++k) o[k] = (T)0;
+            } else if constexpr (RBGS) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) o[k] = W[s - 1][MID][k];     // the other colour is carried over
+                if (rb_kk(rs, s) == 0) {                                 // warp-uniform (see rb_kk)
+#pragma unroll
+                    for (int k = 0; k < V; k += 2) {
+                        const T l = (k == 0) ? WL[s - 1][MID] : W[s - 1][MID][k - 1];
+                        o[k] = gs_pt<T>(ff[k], sigma4<T>(W[s - 1][OLD][k], W[s - 1][NEW][k], l, W[s - 1][MID][k + 1]));
+                        mask_col(o[k], k);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 1; k < V; k += 2) {
+                        const T r = (k == V - 1) ? WR[s - 1][MID] : W[s - 1][MID][k + 1];
+                        o[k] = gs_pt<T>(ff[k], sigma4<T>(W[s - 1][OLD][k], W[s - 1][NEW][k], W[s - 1][MID][k - 1], r));
+                        mask_col(o[k], k);
+                    }
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < V; ++k) {
                     const T l = (k == 0) ? WL[s - 1][MID] : W[s - 1][MID][k - 1];
                     const T r = (k == V - 1) ? WR[s - 1][MID] : W[s - 1][MID][k + 1];
-                    const T sig = sigma4<T>(W[s - 1][OLD][k], W[s - 1][NEW][k], l, r);
-                    if (RBGS) {
-                        const int colour = (s - 1) & 1;
-                        o[k] = (((rs + c + k) & 1) == colour) ? gs_pt<T>(ff[k], sig) : W[s - 1][MID][k];
-                    } else {
-                        o[k] = jacobi_pt<T>(a.c0, a.c1, W[s - 1][MID][k], ff[k], sig);
-                    }
+                    o[k] = jacobi_pt<T>(a.c0, a.c1, W[s - 1][MID][k], ff[k], sigma4<T>(W[s - 1][OLD][k], W[s - 1][NEW][k], l, r));
                 }
                 mask_cols(o);
             }
-            if (s < C::NW) put_row<NEW>(s, o);
+            if (s < C::NW) put_row<NEW>(s, o, (RBGS && s < NS) ? rb_need(rs, s + 1) : 3);
             if (s == NS) {
                 if (lane_st && rs >= y0 && rs < y1) stv<T>(g_o, o);
                 g_o += a.pitch;
@@ -484,28 +429,6 @@ struct Streamer {
             g_c = a.ec + (i64)((ylo + 1) >> 1) * a.pitch_c + (c >> 1);
         }
 
-        if constexpr (TMA) {
-            lane_id = lane;
-            dead_ = dead;
-            y_last = yhi;
-            it = 0;
-            const long long avail = (long long)a.pitch - X0;
-            bytes_u = (unsigned)(avail <= 0 ? 0 : (avail >= 32 * V ? 32 * V : avail)) * (unsigned)sizeof(T);
-            const long long availc = (long long)a.pitch_c - (X0 >> 1);
-            bytes_c = C::HAS_POST ? (unsigned)(availc <= 0 ? 0 : (availc >= 32 * H ? 32 * H : availc)) * (unsigned)sizeof(T) : 0u;
-            mbar = reinterpret_cast<unsigned long long*>(ring_base + (size_t)kStreamWarps * C::WARP_ELEMS) + warp * kRingSlots;
-            // the whole ring starts as zeros (columns beyond the pitch are never written by a bulk copy)
-            T* wbase = ring_base + (size_t)warp * C::WARP_ELEMS;
-            for (int i = lane; i < C::WARP_ELEMS; i += 32) wbase[i] = (T)0;
-            if (lane == 0) {
-#pragma unroll
-                for (int i = 0; i < kRingSlots; ++i) mbar_init(mbar + i, 1);
-                mbar_init_fence();
-            }
-            fence_proxy_async();
-            __syncwarp();
-        }
-
         // prologue: rows ylo .. ylo+D-1 into slots 0 .. D-1
         set_blocks(0);
         issue_prologue<0>(ylo);
@@ -522,20 +445,15 @@ struct Streamer {
             wait_row<2>();
             step<2>(y + 2);
             q = (q + 1) & 3;
-            if constexpr (TMA) ++it;
         }
-        if constexpr (!TMA) cp_async_wait<0>();   // (TMA: nothing is fetched beyond the last consumed row)
+        cp_async_wait<0>();
     }
 
     // the row that step<PH> is about to consume has landed
     template <int PH>
     __device__ __forceinline__ void wait_row()
     {
-        if constexpr (TMA) {
-            mbar_wait(mbar + ((it & 3) * 3 + PH), (unsigned)((it >> 2) & 1));
-        } else {
-            cp_async_wait<C::D>();
-        }
+        cp_async_wait<C::D>();
     }
 
     template <int I>
@@ -548,8 +466,11 @@ struct Streamer {
     }
 };
 
+// launch bound = the 12 resident warps per SM the host caps these kernels at (FusedKnobs::occ): 170 registers per
+// thread instead of the 128 a bound of 16 allows, which the red-black PRE kernel (NS = 4) needs to stay spill-free
+constexpr int kStreamMinCtas = 12;
 template <typename T, int NS, int MODE, bool RBGS>
-__global__ void __launch_bounds__(kStreamWarps * 32, 16 / kStreamWarps)
+__global__ void __launch_bounds__(kStreamWarps * 32, kStreamMinCtas / kStreamWarps)
 k_stream(const StreamArgs<T> a)
 {
     extern __shared__ __align__(16) unsigned char stream_smem[];
@@ -557,19 +478,6 @@ k_stream(const StreamArgs<T> a)
     const int item = blockIdx.x * kStreamWarps + warp;
     Streamer<T, NS, MODE, RBGS> st(a);
     st.run(reinterpret_cast<T*>(stream_smem), warp, threadIdx.x & 31, item);
-}
-
-// TMA variant (opt-in MGB200_TMA=1): same pipeline, rows arrive by bulk copy (UBLKCP) + mbarrier
-constexpr int kStreamTmaExtraSmem = 128;   // kStreamWarps * kRingSlots mbarriers after the rings
-template <typename T, int NS, int MODE, bool RBGS>
-__global__ void __launch_bounds__(kStreamWarps * 32, 12 / kStreamWarps)
-k_stream_tma(const StreamArgs<T> a)
-{
-    extern __shared__ __align__(128) unsigned char stream_tma_smem[];
-    const int warp = threadIdx.x >> 5;
-    const int item = blockIdx.x * kStreamWarps + warp;
-    Streamer<T, NS, MODE, RBGS, false, true> st(a);
-    st.run(reinterpret_cast<T*>(stream_tma_smem), warp, threadIdx.x & 31, item);
 }
 
 // POSTPRE (visit chains, opt-in MGB200_CHAIN=1) needs ~142 registers at NS = 4: its own entry point with a launch bound
@@ -602,7 +510,7 @@ k_stream_fmg_entry(const StreamArgs<T> a)
 // zero-guess variant of the PRE kernel (opt-in, MGB200_ZERO_GUESS=1): a separate kernel so that k_stream itself
 // stays byte-identical to the GPU-verified build
 template <typename T, int NS, bool RBGS>
-__global__ void __launch_bounds__(kStreamWarps * 32, 16 / kStreamWarps)
+__global__ void __launch_bounds__(kStreamWarps * 32, kStreamMinCtas / kStreamWarps)
 k_stream_pre_zg(const StreamArgs<T> a)
 {
     extern __shared__ __align__(16) unsigned char stream_smem[];

@@ -119,6 +119,17 @@ class Multigrid:
     def force_constant(self, f: float = 4.0):
         self._ck(self._lib.mg_force_constant(self._ctx, float(f)))
 
+    def force_synthetic(self, seed: int = 1234):
+        """Benchmark right-hand side generated on the device: b = h^2 (2U-1), U from splitmix64(seed, global index)
+        (mg_force_synthetic; tests/synth_ref.py restates it in numpy)."""
+        self._ck(self._lib.mg_force_synthetic(self._ctx, ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF)))
+
+    def checksum(self, level: int, which: int = 0) -> int:
+        """Order-independent 64-bit checksum of this rank's owned values of u (0), f (1) or r (2) (mg_checksum)."""
+        out = ctypes.c_uint64(0)
+        self._ck(self._lib.mg_checksum(self._ctx, level, which, ctypes.byref(out)))
+        return int(out.value)
+
     def set_rhs(self, level: int, f_h):
         self._ck(self._lib.mg_set_rhs_host(self._ctx, level, _vp(self._vec(level, f_h))))
 
@@ -300,3 +311,4 @@ def comm_id() -> bytes:
     if rc != capi.MG_OK:
         raise capi.MgError(rc, capi.lib().mg_last_error(None).decode())
     return buf.raw
+

@@ -26,6 +26,7 @@ def use_emulated_library():
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: full-size BASELINE configs (GB of host memory, a minute or two); deselect with -m \"gpu and not slow\"")
     if EMULATED:
         use_emulated_library()
 

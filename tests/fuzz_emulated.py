@@ -33,10 +33,9 @@ def main():
         nu1, nu2 = int(rng.integers(0, 5)), int(rng.integers(0, 5))
         gamma = int(rng.integers(1, 4))
         flags = dict(graph=bool(rng.integers(0, 2)), fused=bool(rng.integers(0, 2)), coarse_tail=bool(rng.integers(0, 2)))
-        env = {k: str(int(rng.integers(0, 2))) for k in ("MGB200_TILE", "MGB200_ZERO_GUESS", "MGB200_CTAIL", "MGB200_CHAIN", "MGB200_TMA")}
-        env["MGB200_CTAIL_CTAS"] = str([1, 2, 4, 8, 16][int(rng.integers(0, 5))])
+        env = {k: str(int(rng.integers(0, 2))) for k in ("MGB200_ZERO_GUESS", "MGB200_CHAIN")}
         if os.environ.get("FUZZ_DEFAULT_ONLY") == "1":
-            env = {k: "0" for k in env}
+            env = {k: "1" for k in env}   # the library defaults
         os.environ.update(env)
         cfg = dict(level=level, coarsest=coarsest, dtype=np.dtype(dtype).name, smoother=smoother, nu1=nu1, nu2=nu2, gamma=gamma,
                    **flags, **env)

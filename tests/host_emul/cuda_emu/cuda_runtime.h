@@ -146,6 +146,9 @@ inline T __shfl_down_sync(unsigned, T v, unsigned delta, int = 32)
     emu::shfl_bytes(&v, sizeof(T), (int)delta);
     return v;
 }
+// fibers of one emulated device run one at a time (cooperative scheduling), so a plain read-modify-write is atomic
+template <typename T>
+inline T atomicAdd(T* p, T v) { const T old = *p; *p = old + v; return old; }
 inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
 inline double __longlong_as_double(long long l) { double r; std::memcpy(&r, &l, 8); return r; }
 inline unsigned __float_as_uint(float f) { unsigned r; std::memcpy(&r, &f, 4); return r; }

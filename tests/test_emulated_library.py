@@ -7,9 +7,8 @@ for the NCCL calls).  A child pytest with MGB200_TEST_EMU=1 then runs the `gpu`-
 test_optin_gpu.py and the multi-rank worker unchanged, only pointed at that library (tests/conftest.py).
 
 What this buys: every host-side decision (cycle recursion, ping-pong bookkeeping, graph cache keys, lazy halo
-exchanges, the communication-avoiding plan executor, the zero-guess chain, the cluster-tail op list) and the arithmetic
-of every kernel are checked bit for bit against the oracle on every CPU run -- including the opt-in paths that have not
-been on a GPU yet.  What it cannot show: speed, occupancy, PTX-level behaviour (cp.async, LDGSTS), memory-model races.
+exchanges, the communication-avoiding plan executor, the zero-guess chain, visit chains) and the arithmetic
+of every kernel are checked bit for bit against the oracle on every CPU run.  What it cannot show: speed, occupancy, PTX-level behaviour (cp.async, LDGSTS), memory-model races.
 The real `-m gpu` run on the B200 stays the parity gate; this file is selected by `-m "not gpu"`.
 
 The selections below are sized for the CPU suite (a few minutes in total); drop the -k filters for the full sets
@@ -50,7 +49,7 @@ def torchrun_cmd(world, script, *args):
 WORKER = os.path.join(ROOT, "tests", "mgpu_worker.py")
 BENCH_WORKER = os.path.join(ROOT, "tests", "host_emul", "bench_emu_worker.py")
 KNOBS = {"default": {}, "comm_avoid+graph_dist": {"MGB200_COMM_AVOID": "1", "MGB200_GRAPH_DIST": "1"},
-         "tile+zero_guess": {"MGB200_TILE": "1", "MGB200_ZERO_GUESS": "1"}, "chain+graph_dist": {"MGB200_CHAIN": "1", "MGB200_GRAPH_DIST": "1"},
+         "no_chain_no_zero_guess": {"MGB200_CHAIN": "0", "MGB200_ZERO_GUESS": "0"}, "graph_dist": {"MGB200_GRAPH_DIST": "1"},
          "overlap+graph_dist": {"MGB200_OVERLAP": "1", "MGB200_GRAPH_DIST": "1"}}
 BENCH = {"1rank": (1, []), "2ranks_slab_host_buffers": (2, ["--aggl", "5", "--level", "8"]), "rbgs_wcycle": (1, ["--smoother", "rbgs", "--gamma", "2"])}
 
@@ -66,10 +65,10 @@ class Jobs:
         self.procs = {}
         jobs = {
             "parity": (pytest_cmd(["tests/test_parity_gpu.py", "-k",
-                                   "not 4097 and not cpp_ and not combinations[9- and not 10-float and not iterates_bitwise[9"]), {}),
-            "optin": (pytest_cmd(["tests/test_optin_gpu.py", "-k",
-                                  "(tile_kernels_cycles or zero_guess or cluster_tail or visit_chain or tma_streaming) and not [10- and not [8- and not [9- "
-                                  "and not -8-float and not -1-float"]), {"MGB200_TEST_OPTIN": "1"}),
+                                   "not 4097 and not cpp_ and not combinations[9- and not 10-float and not iterates_bitwise[9 "
+                                   "and not zero_guess and not visit_chain"]), {}),
+            "chains": (pytest_cmd(["tests/test_parity_gpu.py", "-k",
+                                   "(zero_guess or visit_chain) and not -10- and not -8- and not -9- and not 0-10 and not 1-10"]), {}),
             "problem": (pytest_cmd(["tests/test_problem_setup.py"]), {}),
         }
         for name, knobs in KNOBS.items():
@@ -119,10 +118,9 @@ def test_gpu_parity_suite_under_emulation(jobs):
     assert " passed" in out and "failed" not in out
 
 
-def test_optin_paths_under_emulation(jobs):
-    """Tile kernels, zero-guess chain, POST+PRE visit chains and the cluster coarse tail (16- and 4-CTA clusters) through
-    the real host code."""
-    out = jobs.result("optin")
+def test_zero_guess_and_visit_chains_under_emulation(jobs):
+    """Zero-guess chain and POST+PRE visit chains (both default, and switched off) through the real host code."""
+    out = jobs.result("chains")
     assert " passed" in out and "failed" not in out
 
 

@@ -178,6 +178,105 @@ def test_mg_cycles_equals_repeated_cycles(mgb, orc, smoother, gamma):
                 mg.cycles(-1, level)
 
 
+@pytest.fixture
+def knob():
+    saved = {}
+
+    def set_knob(name, value):
+        saved.setdefault(name, os.environ.get(name))
+        os.environ[name] = value
+    yield set_knob
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("smoother,nu1,nu2,gamma", [("jacobi", 2, 2, 1), ("jacobi", 1, 2, 2), ("rbgs", 2, 2, 1), ("rbgs", 1, 1, 2),
+                                                    ("jacobi", 3, 2, 1)])
+@pytest.mark.parametrize("level", [4, 7, 8, 10])
+@pytest.mark.parametrize("zg", ["1", "0"])
+def test_zero_guess_chain_bitwise(mgb, orc, knob, level, dtype, smoother, nu1, nu2, gamma, zg):
+    """Zero-guess chain (default; MGB200_ZERO_GUESS=0 is the A/B switch): PRE skips the zero coarse guess store (P:613), the
+    next level's PRE / the tail do not read u.  Both settings give the oracle's bits."""
+    knob("MGB200_ZERO_GUESS", zg)
+    x, b = rand_vec(level, dtype, 83), rand_vec(level, dtype, 84, 1e-3)
+    p = oracle.Params(nu1=nu1, nu2=nu2, gamma=gamma, smoother=1 if smoother == "rbgs" else 0, nthreads=4)
+    want = [x]
+    for _ in range(3):
+        want.append(orc.vcyclemultigrid(want[-1], b, p))
+    for graph, tail in ((False, False), (False, True), (True, True)):
+        with mgb.Multigrid(level, dtype=dtype, smoother=smoother, graph=graph, fused=True, coarse_tail=tail) as mg:
+            mg.set_u(level, x)
+            mg.set_rhs(level, b)
+            for k in range(3):
+                mg.cycle(level, nu1, nu2, gamma)
+                assert_bitwise(mg.get_u(level), want[k + 1], f"zero-guess cycle {k + 1} graph={graph} tail={tail}")
+            # every API that reads a coarse iterate must see real zeros
+            if level > 2:
+                mg.residual(level)
+                mg.restrict(level)
+                assert not mg.get_u(level - 1).any()
+            pv = oracle.Params(nu1=nu1, nu2=nu2, smoother=p.smoother, nthreads=4)   # mg_fmg runs V-cycles (P:646)
+            assert_bitwise(mg.fullmultigrid(b, 1, nu1, nu2), orc.fullmultigrid(b, 1, pv), "fmg with zero-guess chain")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("smoother,nu1,nu2", [("jacobi", 2, 2), ("jacobi", 1, 1), ("jacobi", 1, 2), ("jacobi", 2, 1), ("jacobi", 3, 1),
+                                              ("rbgs", 1, 1), ("rbgs", 2, 2)])
+@pytest.mark.parametrize("level", [3, 5, 7, 8, 10])
+@pytest.mark.parametrize("chain", ["1", "0"])
+def test_visit_chain_postpre_bitwise(mgb, orc, knob, level, dtype, smoother, nu1, nu2, chain):
+    """Visit chains (default; MGB200_CHAIN=0 is the A/B switch): POST of one visit of a level and PRE of the next visit are one POSTPRE launch -- consecutive cycles
+    through mg_cycles (the loop P:646-648) and the gamma visits of a W-cycle through mg_cycle; fullmultigrid uses it per
+    level.  Same bits as the same number of separate cycles."""
+    knob("MGB200_CHAIN", chain)
+    x, b = rand_vec(level, dtype, 87), rand_vec(level, dtype, 88, 1e-3)
+    sid = 1 if smoother == "rbgs" else 0
+    for gamma, count in ((1, 3), (2, 1), (2, 2)):
+        p = oracle.Params(nu1=nu1, nu2=nu2, gamma=gamma, smoother=sid, nthreads=4)
+        want = [x]
+        for _ in range(2 * count):
+            want.append(orc.vcyclemultigrid(want[-1], b, p))
+        for graph, tail in ((False, False), (True, True)):
+            with mgb.Multigrid(level, dtype=dtype, smoother=smoother, graph=graph, coarse_tail=tail) as mg:
+                mg.set_u(level, x)
+                mg.set_rhs(level, b)
+                mg.cycles(count, level, nu1, nu2, gamma)
+                assert_bitwise(mg.get_u(level), want[count], f"chain g={gamma} n={count} graph={graph} tail={tail}")
+                mg.cycles(count, level, nu1, nu2, gamma)      # replay from the new buffer parities
+                assert_bitwise(mg.get_u(level), want[2 * count], f"chain replay g={gamma} n={count} graph={graph}")
+    # fullmultigrid: the interpolation of the coarse solution (P:645) is fused into the first PRE of each level
+    # (k_stream_fmg_entry), its cycles per level are chained
+    pv = oracle.Params(nu1=nu1, nu2=nu2, smoother=sid, nthreads=4)
+    for graph, tail in ((False, False), (True, True)):
+        with mgb.Multigrid(level, dtype=dtype, smoother=smoother, graph=graph, coarse_tail=tail) as mg:
+            for cyc in (1, 3):
+                assert_bitwise(mg.fullmultigrid(b, cyc, nu1, nu2), orc.fullmultigrid(b, cyc, pv), f"fmg, {cyc} cycles per level")
+            # a pending interpolation must be materialised for any other reader
+            if level > 2:
+                mg.set_rhs(level, b)
+                mg.fmg(1, nu1, nu2)
+                assert_bitwise(mg.get_u(level), orc.fullmultigrid(b, 1, pv), "resident fmg")
+
+
+def test_visit_chain_really_fuses(mgb, knob):
+    """Launch counts: 3 chained V(2,2) cycles at 513^2 save two launches on the finest level, a W-cycle one per level."""
+    counts = {}
+    for chain in ("0", "1"):
+        knob("MGB200_CHAIN", chain)
+        for gamma, n in ((1, 3), (2, 1)):
+            with mgb.Multigrid(9, graph=False) as mg:
+                mg.force_constant(4.0)
+                mg.zero_u(9)
+                l0 = mg.launches
+                mg.cycles(n, 9, 2, 2, gamma)
+                counts[chain, gamma] = mg.launches - l0
+    assert counts["1", 1] == counts["0", 1] - 2 and counts["1", 2] < counts["0", 2]
+
+
 def test_golden_fixtures(mgb):
     """Committed oracle outputs (tests/golden/oracle_golden.npz, made by make_golden.py)."""
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.npz"))
