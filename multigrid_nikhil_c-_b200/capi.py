@@ -8,7 +8,8 @@ import re
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmgb200.so")
+# MGB200_LIB: development hook for A/B timing of two builds of the same sources (tools/gpu_*.sh); never a CPU path
+LIB_PATH = os.environ.get("MGB200_LIB") or os.path.join(_HERE, "lib", "libmgb200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mgb200.h")
 
 MG_OK, MG_ERR_ARG, MG_ERR_CUDA, MG_ERR_STATE, MG_ERR_COMM, MG_ERR_ALLOC = range(6)

@@ -48,7 +48,12 @@ constexpr bool mode_has_pre(int m) { return m == MODE_PRE || m == MODE_POSTPRE; 
 
 constexpr int kStreamWarps = 1;  // warps (independent work items) per CTA.  4 lock-stepped warps per CTA (bar.sync every 3 rows)
                                  // were measured slower and more erratic (profiles/r01_tune_stream.txt)
-constexpr int kRingSlots = 12;   // 4 blocks x 3 slots
+// ring slots per warp: NB blocks of 3 slots, NB a power of two.  12 slots prefetch D = 9 - NS rows ahead; the deep ring
+// (24 slots, D = 21 - NS) keeps more bytes in flight per warp at the price of fewer resident warps (shared memory).
+#ifndef MGB_DEEP_RING_MIN_NS
+#define MGB_DEEP_RING_MIN_NS 99   // kernels with NS >= this use the deep ring (build-time experiment switch)
+#endif
+constexpr int ring_slots(int ns) { return ns >= MGB_DEEP_RING_MIN_NS ? 24 : 12; }
 
 template <typename T, int NS, int MODE>
 struct StreamCfg {
@@ -61,7 +66,8 @@ struct StreamCfg {
     static constexpr int OUTW = 32 * V - 2 * V * HLANES;                                // output columns per strip
     static constexpr int HT = NS + (HAS_PRE ? 2 : 0) + (HAS_POST ? 1 : 0);              // rows needed above
     static constexpr int HB = NS + (HAS_PRE ? 2 : 0);                                   // rows needed below
-    static constexpr int DEPTH = kRingSlots;
+    static constexpr int DEPTH = ring_slots(NS);
+    static constexpr int NB = DEPTH / 3;                                                // ring blocks (power of two)
     static constexpr int D = DEPTH - NS - 3;                                            // prefetch distance (rows)
     static constexpr int NW = NS + (HAS_PRE ? 1 : 0);                                   // register windows of u_s
     // slot: [u: 32 V][f: 32 V]; POST keeps the coarse rows in a second, half-rate ring
@@ -133,8 +139,9 @@ struct Streamer {
     const StreamArgs<T>& a;
     T* ring;       // this lane's 16 bytes of slot 0 (u part)
     T* cring;      // POST: this lane's 8 bytes of coarse slot 0
-    T* blk[4];     // blk[j] = ring block (q + j) & 3 for the current outer iteration q
-    T* cblk[4];
+    static constexpr int NB = C::NB;
+    T* blk[NB];    // blk[j] = ring block (q + j) & (NB - 1) for the current outer iteration q
+    T* cblk[NB];
     int c;         // first column of this lane
     int y0, y1;
     bool lane_ld, lane_ldc, lane_st;  // per-lane load / store flags
@@ -160,7 +167,7 @@ struct Streamer {
         constexpr int rel = PH - BACK;                       // slot index relative to this iteration's block
         constexpr int b = (rel >= 0) ? rel / 3 : -((-rel + 2) / 3);
         constexpr int s = rel - 3 * b;
-        return blk[(b + 4) & 3] + s * C::SLOT_ELEMS;
+        return blk[(b + NB) & (NB - 1)] + s * C::SLOT_ELEMS;
     }
     template <int PH, int BACK>
     __device__ __forceinline__ T* cslot() const
@@ -168,7 +175,7 @@ struct Streamer {
         constexpr int rel = PH - BACK;
         constexpr int b = (rel >= 0) ? rel / 3 : -((-rel + 2) / 3);
         constexpr int s = rel - 3 * b;
-        return cblk[(b + 4) & 3] + s * C::CSLOT_ELEMS;
+        return cblk[(b + NB) & (NB - 1)] + s * C::CSLOT_ELEMS;
     }
 
     // prefetch row y into the slot that is REL slots ahead of this iteration's block start
@@ -176,7 +183,7 @@ struct Streamer {
     __device__ __forceinline__ void issue(int y)
     {
         constexpr int b = REL / 3, s = REL % 3;
-        T* dst = blk[b & 3] + s * C::SLOT_ELEMS;
+        T* dst = blk[b & (NB - 1)] + s * C::SLOT_ELEMS;
         const bool v = lane_ld && (y >= a.row_lo) && (y < a.row_hi);
         if (!ZG) cp_async16(dst, v ? g_u : safe_u, v);
         cp_async16(dst + 32 * V, v ? g_f : safe_f, v);
@@ -186,7 +193,7 @@ struct Streamer {
             // coarse row ceil(y/2): a new one starts at every odd y; even rows re-read the previous one (L1 hit)
             const int ic = (y + 1) >> 1;
             const bool vc = lane_ldc && (ic >= a.crow_lo) && (ic < a.crow_hi) && (y >= 0);
-            cp_async8(cblk[b & 3] + s * C::CSLOT_ELEMS, vc ? g_c : safe_c, vc);
+            cp_async8(cblk[b & (NB - 1)] + s * C::CSLOT_ELEMS, vc ? g_c : safe_c, vc);
             if (!(y & 1)) g_c += a.pitch_c;   // ceil((y+1)/2) > ceil(y/2) exactly when y is even
         }
         cp_async_commit();
@@ -375,9 +382,9 @@ struct Streamer {
     __device__ __forceinline__ void set_blocks(int q)
     {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            blk[j] = ring + ((q + j) & 3) * BLK;
-            if (C::HAS_POST) cblk[j] = cring + ((q + j) & 3) * CBLK;
+        for (int j = 0; j < NB; ++j) {
+            blk[j] = ring + ((q + j) & (NB - 1)) * BLK;
+            if (C::HAS_POST) cblk[j] = cring + ((q + j) & (NB - 1)) * CBLK;
         }
     }
 
@@ -444,7 +451,7 @@ struct Streamer {
             issue<C::D + 2>(y + 2 + C::D);
             wait_row<2>();
             step<2>(y + 2);
-            q = (q + 1) & 3;
+            q = (q + 1) & (NB - 1);
         }
         cp_async_wait<0>();
     }

@@ -50,6 +50,18 @@ class StubMG:
     def force_constant(self, f):
         pass
 
+    def force_synthetic(self, seed=1234):
+        pass
+
+    def checksum(self, level, which=0):
+        return 0x1234 if self.world == 1 else 0x1234 // self.world + (0x1234 % self.world if self.rank == 0 else 0)
+
+    def cycle(self, level=None, nu1=2, nu2=2, gamma=1):
+        self._launches += 13
+
+    def cycles(self, count, level=None, nu1=2, nu2=2, gamma=1):
+        self._launches += 13 * count
+
     def time_cycle(self, level, nu1, nu2, gamma, reps):
         self._launches += 13 * reps
         return 0.3 * reps * 4.0 ** (level - 12)
@@ -86,7 +98,7 @@ class StubMG:
 def _args(**kw):
     d = dict(gpus=1, steps=3, warmup=1, impl="ours", level=6, dtype="f64", smoother="jacobi", nu1=2, nu2=2, gamma=1,
              no_graph=False, no_fused=False, no_tail=False, no_cpu=True, aggl=0, no_e2e=False, full_host_vectors=False, no_n1=False,
-             micro=False)
+             no_extra=False, micro=False)
     d.update(kw)
     return argparse.Namespace(**d)
 
@@ -110,6 +122,7 @@ def test_bench_control_flow_and_json_contract(monkeypatch, world):
         import torch.distributed as dist
         monkeypatch.setattr(dist, "init_process_group", lambda *a, **k: None)
         monkeypatch.setattr(dist, "broadcast_object_list", lambda *a, **k: None)
+        monkeypatch.setattr(dist, "all_gather_object", lambda lst, obj: lst.__setitem__(slice(None), [obj] + [0] * (len(lst) - 1)))
         monkeypatch.setattr(dist, "barrier", lambda *a, **k: None)
         monkeypatch.setattr(dist, "all_reduce", lambda *a, **k: None)
         monkeypatch.setattr(dist, "destroy_process_group", lambda *a, **k: None)
@@ -125,7 +138,13 @@ def test_bench_control_flow_and_json_contract(monkeypatch, world):
     assert d["metric"] == bench.METRIC and d["higher_is_better"] is True and d["n_gpus"] == world
     assert set(["bound", "achieved", "peak", "unit", "frac", "traffic"]) <= set(d["roofline"])
     assert set(["value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"]) <= set(d["e2e"])
-    assert d["gpu_launches"] > 0 and "workload" in d["config"]
+    assert d["gpu_launches"] > 0 and "workload" in d["config"] and d["isolated_cycle_ms"] > 0
+    if world > 1:
+        ss = d["strong_scaling"]
+        assert set(["n1_ms_per_step", "speedup", "efficiency", "mgpu_parity", "checksum_1gpu", "checksum_ngpu"]) <= set(ss)
+        assert d["config"]["smoother"] == "jacobi"     # explicit --smoother wins; the default at N > 1 is rbgs
+        assert bench.default_workload(_args(level=0, smoother=None), 2) == (14, "rbgs")
+        assert bench.default_workload(_args(level=0, smoother=None), 1) == (12, "jacobi")
 
 
 def test_updates_per_cycle_matches_survey():
@@ -140,6 +159,29 @@ def test_reference_arm_line(capsys):
     assert d["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
     bench.run_reference(_args(impl="reference", level=6), rank=1, world=2)    # other ranks print nothing
     assert capsys.readouterr().out == ""
+    # N > 1: the SAME workload string as our arm (the driver compares them), RB-GS, all host cores despite torchrun's
+    # OMP_NUM_THREADS=1, right-hand side = the host restatement of the device generator
+    import os
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        bench.run_reference(_args(impl="reference", level=6, smoother=None, steps=2, warmup=1), rank=0, world=2)
+    finally:
+        os.environ.pop("OMP_NUM_THREADS", None)
+    d2 = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert d2["config"]["workload"] == bench.workload_name(6, "f64", 2, 2, 1, "rbgs")
+    assert d2["cpu_baseline"]["cores"] == bench.host_threads()
+
+
+def test_device_synthetic_rows_match_the_test_restatement():
+    import synth_ref
+    for level, dtype in ((5, np.float64), (7, np.float32)):
+        n = (1 << level) - 1
+        out = np.empty(n * n, dtype=dtype)
+        bench.device_synthetic_rows(level, 1, n + 1, dtype, out)
+        assert np.array_equal(out, synth_ref.synthetic_rhs(level, 1234, dtype))
+        part = np.empty(5 * n, dtype=dtype)
+        bench.device_synthetic_rows(level, 4, 9, dtype, part)
+        assert np.array_equal(part, out.reshape(n, n)[3:8].reshape(-1))
 
 
 def test_micro_benchmark_line(monkeypatch, capsys):

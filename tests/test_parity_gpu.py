@@ -277,6 +277,31 @@ def test_visit_chain_really_fuses(mgb, knob):
     assert counts["1", 1] == counts["0", 1] - 2 and counts["1", 2] < counts["0", 2]
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("level", [1, 3, 6, 9])
+def test_synthetic_rhs_and_checksum_match_their_numpy_restatements(mgb, level, dtype):
+    """mg_force_synthetic / mg_checksum (bench.py's device-side right-hand side and its multi-GPU parity record) against
+    tests/synth_ref.py, bit for bit; the checksum is sensitive to a single flipped bit and to a swap of two values."""
+    import synth_ref
+    with make(mgb, level, dtype) as mg:
+        mg.force_synthetic(1234)
+        f = mg.get_rhs(level)
+        assert_bitwise(f, synth_ref.synthetic_rhs(level, 1234, dtype), "synthetic rhs")
+        assert mg.checksum(level, 1) == synth_ref.checksum(level, f)
+        x = rand_vec(level, dtype, 7)
+        mg.set_u(level, x)
+        assert mg.checksum(level, 0) == synth_ref.checksum(level, x)
+        if x.size >= 2:
+            y = x.copy()
+            y[0], y[1] = x[1], x[0]
+            mg.set_u(level, y)
+            assert mg.checksum(level, 0) == synth_ref.checksum(level, y) != synth_ref.checksum(level, x)
+        y = x.copy()
+        y.view(np.uint64 if dtype == np.float64 else np.uint32)[x.size // 2] ^= 1
+        mg.set_u(level, y)
+        assert mg.checksum(level, 0) != synth_ref.checksum(level, x)
+
+
 def test_golden_fixtures(mgb):
     """Committed oracle outputs (tests/golden/oracle_golden.npz, made by make_golden.py)."""
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.npz"))
