@@ -28,13 +28,15 @@
 extern "C" {
 #endif
 
-#define MGB200_VERSION 100
+#define MGB200_VERSION 200
 
 typedef struct mg_ctx mg_ctx;
 
 enum { MG_OK = 0, MG_ERR_ARG = 1, MG_ERR_CUDA = 2, MG_ERR_STATE = 3, MG_ERR_COMM = 4, MG_ERR_ALLOC = 5 };
 enum { MG_F64 = 0, MG_F32 = 1 };                 /* reference P is fp32 (E11), M is fp64 */
 enum { MG_SMOOTH_JACOBI = 0, MG_SMOOTH_RBGS = 1 };
+enum { MG_COARSE_SWEEPS = 0, /* coarsest level: nu1 + nu2 smoothing sweeps (P:583-587)                                  */
+       MG_COARSE_EXACT = 1   /* coarsest level: exact solve, no smoothing (direct_solver M:63-72, called at M:136-139) */ };
 enum { MG_GRAPH = 1,        /* replay whole cycles as CUDA graphs                         */
        MG_FUSED = 2,        /* use the fused / temporally blocked kernels where they apply */
        MG_COARSE_TAIL = 4   /* run the levels that fit one CTA's shared memory in one launch */ };
@@ -55,6 +57,7 @@ typedef struct mg_config {
     int rank, world;           /* this context owns slab `rank` of `world`                  */
     int agglomerate_level;     /* levels <= this are solved redundantly on every rank; 0 = auto */
     const void* comm_id;       /* mg_comm_id() bytes from rank 0, required when world > 1   */
+    int coarse_solver;         /* MG_COARSE_SWEEPS (P:583-587) | MG_COARSE_EXACT (M:63-72; coarsest_level <= 9) */
 } mg_config;
 
 void mg_config_default(mg_config* cfg);

@@ -44,6 +44,7 @@ struct parameters {
     double f = 4.0;            // P:123
     int gamma = 1;             // 1 = V-cycle (reference); 2 = W-cycle
     int smoother = MG_SMOOTH_JACOBI;
+    int coarse_solver = MG_COARSE_SWEEPS;   // P:583-587; MG_COARSE_EXACT = the second version's direct_solver (M:63-72, M:136-139)
 };
 
 struct level { int index; };  // stands in for matrix_elements_for_jacobi (P:24-30)
@@ -62,6 +63,7 @@ public:
         cfg.dtype = std::is_same<T, double>::value ? MG_F64 : MG_F32;
         cfg.smoother = p.smoother;
         cfg.omega = p.omega;
+        cfg.coarse_solver = p.coarse_solver;
         cfg.device = device;
         if (mg_create(&ctx, &cfg) != MG_OK) throw std::runtime_error(std::string("mg_create: ") + mg_last_error(nullptr));
     }
@@ -182,8 +184,9 @@ std::vector<T> globalforcefunction(queue<T>& q, F f, G g)
 // ---------------------------------------------------------------------------------------------
 // the call shape of the reference's second sketch (Multigrid_functions.cpp, "M:"):
 // a problem object with a per-level load-vector dictionary (M:16-26), explicit level arguments, and
-// multigrid_solver(obj) (M:193-197).  Operators are the structured-grid ones of libmgb200; the
-// coarsest level is smoothed (P:583-587), there is no sparse-LU solve (M:63-72: DESIGN.md section 8).
+// multigrid_solver(obj) (M:193-197).  Operators are the structured-grid ones of libmgb200; like the second
+// version, the coarsest level is solved directly (M:63-72, M:136-139: MG_COARSE_EXACT) -- set
+// par.coarse_solver = MG_COARSE_SWEEPS for the first version's nu1+nu2 sweeps there (P:583-587).
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 struct ProblemVar {
@@ -198,6 +201,7 @@ struct ProblemVar {
         p.mu0 = 2;             // M:46
         p.mu1 = 1;             // M:47
         p.mu2 = 1;             // M:48
+        p.coarse_solver = MG_COARSE_EXACT;   // M:136-139
         return p;              // omega: M:49 `4 / 5` is integer 0 (erratum); P:127's 2/3 is kept
     }
 };

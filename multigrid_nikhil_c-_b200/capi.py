@@ -16,6 +16,7 @@ MG_OK, MG_ERR_ARG, MG_ERR_CUDA, MG_ERR_STATE, MG_ERR_COMM, MG_ERR_ALLOC = range(
 MG_F64, MG_F32 = 0, 1
 MG_SMOOTH_JACOBI, MG_SMOOTH_RBGS = 0, 1
 MG_GRAPH, MG_FUSED, MG_COARSE_TAIL = 1, 2, 4
+MG_COARSE_SWEEPS, MG_COARSE_EXACT = 0, 1
 MG_COMM_ID_BYTES = 128
 (MG_INFO_PITCH, MG_INFO_ROWS_STORED, MG_INFO_ROW_BEGIN, MG_INFO_ROW_END, MG_INFO_LAUNCHES,
  MG_INFO_DISTRIBUTED, MG_INFO_BYTES_ALLOCATED, MG_INFO_GRAPH_LAUNCHES, MG_INFO_AGGLOMERATE_LEVEL,
@@ -30,6 +31,7 @@ class MgConfig(ctypes.Structure):
         ("smoother", ctypes.c_int), ("omega", ctypes.c_double), ("restrict_weight", ctypes.c_double),
         ("device", ctypes.c_int), ("flags", ctypes.c_int), ("rank", ctypes.c_int), ("world", ctypes.c_int),
         ("agglomerate_level", ctypes.c_int), ("comm_id", ctypes.c_void_p),
+        ("coarse_solver", ctypes.c_int),
     ]
 
 

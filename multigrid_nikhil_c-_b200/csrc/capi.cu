@@ -52,6 +52,7 @@ void mg_config_default(mg_config* cfg)
     cfg->world = 1;
     cfg->agglomerate_level = 0;
     cfg->comm_id = nullptr;
+    cfg->coarse_solver = MG_COARSE_SWEEPS;   // P:583-587
 }
 
 int mg_create(mg_ctx** out, const mg_config* cfg)

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "coarse.cuh"
 #include "comm.cuh"
 #include "fused.cuh"
 #include "sched.h"
@@ -52,6 +53,9 @@ void Ctx::init()
                "coarsest_level must be in 1..finest_level");
     MG_REQUIRE(cfg.dtype == MG_F64 || cfg.dtype == MG_F32, "dtype must be MG_F64 or MG_F32");
     MG_REQUIRE(cfg.smoother == MG_SMOOTH_JACOBI || cfg.smoother == MG_SMOOTH_RBGS, "unknown smoother");
+    MG_REQUIRE(cfg.coarse_solver == MG_COARSE_SWEEPS || cfg.coarse_solver == MG_COARSE_EXACT, "unknown coarse_solver");
+    MG_REQUIRE(!exact_coarse() || cfg.coarsest_level <= kCoarseExactMaxLevel,
+               "MG_COARSE_EXACT needs coarsest_level <= 9 (the sine-transform table is n x n)");
     MG_REQUIRE(cfg.world >= 1 && cfg.rank >= 0 && cfg.rank < cfg.world, "bad rank/world");
     MG_REQUIRE((cfg.world & (cfg.world - 1)) == 0, "world must be a power of two");
     esize = f64() ? 8 : 4;
@@ -150,6 +154,30 @@ void Ctx::init()
         MG_CK(cudaMalloc(&d_norm, sizeof(double) * 8));
         MG_CK(cudaMallocHost(&h_norm, sizeof(double) * 8));
     }
+    if (exact_coarse()) {
+        // sine-transform tables of the coarsest level, formed in double with the oracle's expressions, rounded to T once
+        MG_REQUIRE(!levels[cfg.coarsest_level].distributed, "MG_COARSE_EXACT needs a replicated coarsest level");
+        const int n = (1 << cfg.coarsest_level) - 1;
+        const double pi = 3.14159265358979323846;
+        std::vector<double> S((size_t)n * n), d(n);
+        for (int j = 0; j < n; ++j) {
+            d[j] = 2.0 - 2.0 * std::cos(pi * (double)(j + 1) / (double)(n + 1));
+            for (int k = 0; k < n; ++k) {
+                const long p = ((long)(j + 1) * (long)(k + 1)) % (2L * (n + 1));   // exact period of the argument
+                S[(size_t)j * n + k] = std::sin(pi * (double)p / (double)(n + 1));
+            }
+        }
+        MG_CK(cudaMalloc(&d_dst_S, S.size() * esize));
+        MG_CK(cudaMalloc(&d_dst_d, d.size() * esize));
+        if (f64()) {
+            MG_CK(cudaMemcpy(d_dst_S, S.data(), S.size() * 8, cudaMemcpyHostToDevice));
+            MG_CK(cudaMemcpy(d_dst_d, d.data(), d.size() * 8, cudaMemcpyHostToDevice));
+        } else {
+            std::vector<float> Sf(S.begin(), S.end()), df(d.begin(), d.end());
+            MG_CK(cudaMemcpy(d_dst_S, Sf.data(), Sf.size() * 4, cudaMemcpyHostToDevice));
+            MG_CK(cudaMemcpy(d_dst_d, df.data(), df.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
     if (cfg.world > 1) {
         comm = comm_create(*this);
         const char* e = getenv("MGB200_GRAPH_DIST");
@@ -190,6 +218,9 @@ void Ctx::release() noexcept
         for (int k = 0; k < 4; ++k)
             if (lv.alloc[k]) cudaFree(lv.alloc[k]);
     if (d_partials) cudaFree(d_partials);
+    if (d_dst_S) cudaFree(d_dst_S);
+    if (d_dst_d) cudaFree(d_dst_d);
+    d_dst_S = d_dst_d = nullptr;
     if (d_norm) cudaFree(d_norm);
     if (h_norm) cudaFreeHost(h_norm);
     if (stream) cudaStreamDestroy(stream);
@@ -417,15 +448,7 @@ double Ctx::residual_t(int level, bool want_norm, bool store)
     MG_REQUIRE(!capturing, "norm read-back inside a captured cycle");
     launch_sum_partials(stream, lc, d_partials, np, d_norm);
     MG_CK(cudaGetLastError());
-    double sumsq = 0.0;
-    if (lv.distributed) {
-        sumsq = comm_sum(*this, d_norm);  // fixed rank order => same value on every rank
-    } else {
-        MG_CK(cudaMemcpyAsync(h_norm, d_norm, sizeof(double), cudaMemcpyDeviceToHost, stream));
-        MG_CK(cudaStreamSynchronize(stream));
-        sumsq = h_norm[0];
-    }
-    return std::sqrt(sumsq);
+    return read_norm(lv);
 }
 
 template <typename T>
@@ -476,6 +499,39 @@ void Ctx::prolong_t(int fine_level, bool add)
     lf.hv_u = 0;
 }
 
+// u = A^-1 f on the coarsest level (see coarse.cuh).  Scratch: r and the non-current u buffer of that level (interior
+// only: their zero rings stay intact, and every later writer of those arrays overwrites the whole interior).
+template <typename T>
+static void coarse_exact_t(Ctx& ctx, Level& lv)
+{
+    const int n = lv.N - 1;
+    const i64 P = lv.pitch;
+    const T* S = (const T*)ctx.d_dst_S;
+    const T* d = (const T*)ctx.d_dst_d;
+    auto interior = [&](char* base) { return (T*)base + P + 1; };
+    const T* F = interior(lv.f);
+    T* t1 = interior(lv.r);
+    T* t2 = interior(lv.u[lv.cur ^ 1]);
+    T* U = interior(lv.u[lv.cur]);
+    const T c = (T)(4.0 / ((double)(n + 1) * (double)(n + 1)));
+    launch_dense_product<T, 0>(ctx.stream, ctx.lc, F, P, S, n, t1, P, n, d, c);     // t1 = F S
+    launch_dense_product<T, 1>(ctx.stream, ctx.lc, S, n, t1, P, t2, P, n, d, c);    // t2 = (S t1) ./ Lambda
+    launch_dense_product<T, 0>(ctx.stream, ctx.lc, t2, P, S, n, t1, P, n, d, c);    // t1 = t2 S
+    launch_dense_product<T, 2>(ctx.stream, ctx.lc, S, n, t1, P, U, P, n, d, c);     // u = c (S t1)
+    MG_CK(cudaGetLastError());
+}
+
+void Ctx::coarse_exact(int level)
+{
+    Level& lv = L(level);
+    MG_REQUIRE(exact_coarse() && level == cfg.coarsest_level && !lv.distributed, "coarse_exact: not the (replicated) coarsest level");
+    lv.u_zero = lv.u_interp = false;     // the incoming iterate is ignored (M:137), the result overwrites it
+    if (f64()) coarse_exact_t<double>(*this, lv);
+    else coarse_exact_t<float>(*this, lv);
+    lv.hv_u = lv.halo;
+    lv.hv_r = 0;
+}
+
 void Ctx::smooth(int level, int nu) { f64() ? smooth_t<double>(level, nu) : smooth_t<float>(level, nu); }
 double Ctx::residual(int level, bool want_norm, bool store)
 {
@@ -497,6 +553,10 @@ void Ctx::prolong(int fine_level, bool add)
 // ---------------------------------------------------------------------------------
 void Ctx::cycle_rec(int level, int nu1, int nu2, int gamma)
 {
+    if (level <= cfg.coarsest_level && exact_coarse()) {    // M:136-139: direct solve, no smoothing on this level
+        coarse_exact(level);
+        return;
+    }
     if (fused_cycle_level(*this, level, nu1, nu2, gamma)) return;  // fused pre/post kernels or coarse tail
     smooth(level, nu1);                                     // P:581
     if (level <= cfg.coarsest_level) {                      // P:583
@@ -534,7 +594,7 @@ void Ctx::cycles(int level, int nu1, int nu2, int gamma, int count)
         cycle_rec_visits(level, nu1, nu2, gamma, count);
         return;
     }
-    auto key = std::make_tuple(level, nu1, nu2, gamma + 1000 * count, state_blob());
+    auto key = std::make_tuple(level, nu1, nu2, gamma + 1000 * count + (want_post_norm ? 500 : 0), state_blob());
     auto it = graphs.find(key);
     if (it == graphs.end()) {
         fused_pretune(*this, level, nu1, nu2, gamma);
@@ -555,6 +615,7 @@ void Ctx::cycles(int level, int nu1, int nu2, int gamma, int count)
         MG_CK(cudaStreamEndCapture(stream, &g));
         ge.kernels = lc.n - before;
         ge.state_after = state_blob();
+        ge.post_norm = post_norm_done;
         cudaError_t ie = cudaGraphInstantiate(&ge.exec, g, 0);
         cudaGraphDestroy(g);
         if (ie != cudaSuccess) throw MgError(MG_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
@@ -565,6 +626,7 @@ void Ctx::cycles(int level, int nu1, int nu2, int gamma, int count)
     lc.n += it->second.kernels;
     ++graph_launches;
     set_state(it->second.state_after);
+    if (want_post_norm) post_norm_done = it->second.post_norm;
 }
 
 void Ctx::cycle(int level, int nu1, int nu2, int gamma) { cycles(level, nu1, nu2, gamma, 1); }
@@ -584,6 +646,23 @@ void Ctx::fmg(int cycles, int nu1, int nu2)
     }
 }
 
+// sqrt of the sum over the ranks of the sum r^2 a kernel left in d_norm
+double Ctx::read_norm(const Level& lv)
+{
+    double sumsq = 0.0;
+    if (lv.distributed) {
+        sumsq = comm_sum(*this, d_norm);  // fixed rank order => same value on every rank
+    } else {
+        MG_CK(cudaMemcpyAsync(h_norm, d_norm, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        MG_CK(cudaStreamSynchronize(stream));
+        sumsq = h_norm[0];
+    }
+    return std::sqrt(sumsq);
+}
+
+// Tolerance-controlled loop (the reference runs a fixed count, P:635).  The norm after each cycle comes out
+// of the cycle's own last kernel on the finest level when the fused POST applies (k_stream_norm: no extra pass over the
+// grid); otherwise from a residual pass without the store.
 int Ctx::solve(double rtol, int max_cycles, int nu1, int nu2, int gamma, double* relres, double* history)
 {
     const int top = cfg.finest_level;
@@ -592,9 +671,17 @@ int Ctx::solve(double rtol, int max_cycles, int nu1, int nu2, int gamma, double*
     int k = 0;
     double rk = r0;
     while (k < max_cycles) {
-        cycle(top, nu1, nu2, gamma);
+        want_post_norm = true;
+        post_norm_done = false;
+        try {
+            cycle(top, nu1, nu2, gamma);
+        } catch (...) {
+            want_post_norm = false;
+            throw;
+        }
+        want_post_norm = false;
         ++k;
-        rk = residual(top, true, false);
+        rk = post_norm_done ? read_norm(L(top)) : residual(top, true, false);
         if (history) history[k] = rk;
         if (r0 == 0.0 || rk <= rtol * r0) break;
     }

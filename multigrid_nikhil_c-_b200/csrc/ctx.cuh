@@ -110,6 +110,7 @@ struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
     long long kernels = 0;
     std::string state_after;   // Ctx::state_blob() once the captured cycle has run
+    bool post_norm = false;    // the captured cycle's last kernel also produced the residual norm
 };
 
 struct Ctx {
@@ -126,6 +127,8 @@ struct Ctx {
     int partials_cap = 0;
     double* d_norm = nullptr;
     double* h_norm = nullptr;  // pinned
+    void* d_dst_S = nullptr;   // MG_COARSE_EXACT: sine-transform table of the coarsest level (n x n) ...
+    void* d_dst_d = nullptr;   // ... and the 1-D eigenvalues d[j] (coarse.cuh)
     bool capturing = false;
     std::map<std::tuple<int, int, int, int, std::string>, GraphEntry> graphs;
     std::map<std::tuple<int, int, int, int>, int> stream_ry;  // tuned chunk height per (level, mode, NS, rbgs)
@@ -136,6 +139,8 @@ struct Ctx {
     bool zero_guess = true;   // skip reading / writing the zero coarse guess (P:613) where the next kernel does not need it (MGB200_ZERO_GUESS=0 turns it off)
     bool comm_avoid = false;  // communication-avoiding slab schedule (MGB200_COMM_AVOID=1, csrc/sched.h)
     bool overlap = false;     // halo exchange on a second stream, overlapped with the interior rows (MGB200_OVERLAP=1)
+    // tolerance loop: the cycle's last kernel on the finest level also leaves sum r^2 in d_norm (fused.cu: launch_post_norm)
+    bool want_post_norm = false, post_norm_done = false;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool chain = true;        // fuse POST of one visit of a level with PRE of the next (stream.cuh MODE_POSTPRE; MGB200_CHAIN=0 turns it off)
@@ -163,6 +168,8 @@ struct Ctx {
     double residual(int level, bool want_norm, bool store);
     void restrict_to(int fine_level, bool from_rhs);
     void prolong(int fine_level, bool add);
+    void coarse_exact(int level);                            // direct solve on the coarsest level (M:63-72), coarse.cuh
+    bool exact_coarse() const { return cfg.coarse_solver == MG_COARSE_EXACT; }
 
     // cycles
     void cycle(int level, int nu1, int nu2, int gamma);
@@ -172,6 +179,7 @@ struct Ctx {
     void fmg(int cycles, int nu1, int nu2);
     int solve(double rtol, int max_cycles, int nu1, int nu2, int gamma, double* relres, double* history);
     float time_op(int op, int level, int reps);
+    double read_norm(const Level& lv);
 
     void sync();
     void ensure_halo(Level& lv, Which w, int depth);

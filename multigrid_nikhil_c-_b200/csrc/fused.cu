@@ -48,6 +48,10 @@ template <typename T>
 static void set_attrs_chain()
 {
     const int big = 100 * 1024;
+    MG_CK(cudaFuncSetAttribute(k_stream_norm<T, 1, MODE_POST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MG_CK(cudaFuncSetAttribute(k_stream_norm<T, 2, MODE_POST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MG_CK(cudaFuncSetAttribute(k_stream_norm<T, 2, MODE_POST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MG_CK(cudaFuncSetAttribute(k_stream_norm<T, 4, MODE_POST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     MG_CK(cudaFuncSetAttribute(k_stream_chain<T, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -100,10 +104,10 @@ static int default_ry(const Ctx& ctx, const Level& lv, int strips)
     return (ry + 1) & ~1;
 }
 
-template <typename T, int NS, int MODE>
+template <typename T, int NS, int MODE, bool NORM = false>
 static StreamArgs<T> make_args(Ctx& ctx, Level& lv, Level* lcv, int ry, int ya = -1, int yb = -1, bool write_zero_guess = true)
 {
-    typedef StreamCfg<T, NS, MODE> C;
+    typedef StreamCfg<T, NS, MODE, NORM> C;
     StreamArgs<T> a;
     a.u_in = (const T*)lv.u[lv.cur];
     a.u_out = (T*)lv.u[lv.cur ^ 1];
@@ -413,10 +417,40 @@ static void pre_fused(Ctx& ctx, Level& lv, Level& lcv, int nu1)
     }
 }
 
+// POST with the residual norm of its output folded in (k_stream_norm): the last kernel of a cycle on the finest level
+// when the tolerance loop asked for the norm (Ctx::solve).  Leaves sum r^2 of this rank's rows in ctx.d_norm.
+template <typename T, int NS, bool RBGS>
+static bool launch_post_norm(Ctx& ctx, Level& lv, Level* lcv)
+{
+    typedef StreamCfg<T, NS, MODE_POST, true> C;
+    const int ry = tuned_ry<T, NS, MODE_POST, RBGS>(ctx, lv, lcv);
+    ctx.materialize_u(lv);
+    ctx.materialize_u(*lcv);
+    StreamArgs<T> a = make_args<T, NS, MODE_POST, true>(ctx, lv, lcv, ry);
+    if (a.nitems > ctx.partials_cap || a.yb <= a.ya) return false;
+    ctx.ensure_halo(lv, Ctx::W_U, C::HT - 1);
+    ctx.ensure_halo(lv, Ctx::W_F, NS);
+    ctx.ensure_halo(*lcv, Ctx::W_U, (NS + 2) / 2 + 1);
+    k_stream_norm<T, NS, MODE_POST, RBGS><<<cdiv(a.nitems, kStreamWarps), kStreamWarps * 32, stream_smem<C>(ctx), ctx.stream>>>(a, ctx.d_partials);
+    ++ctx.lc.n;
+    MG_CK(cudaGetLastError());
+    launch_sum_partials(ctx.stream, ctx.lc, ctx.d_partials, a.nitems, ctx.d_norm);
+    MG_CK(cudaGetLastError());
+    lv.cur ^= 1;
+    lv.hv_u = 0;
+    return true;
+}
+
 template <typename T>
 static void post_fused(Ctx& ctx, Level& lv, Level& lcv, int nu2)
 {
     const int k = std::min(nu2, 2);
+    if (ctx.want_post_norm && lv.level == ctx.cfg.finest_level && nu2 == k && !ctx.overlap) {
+        bool done;
+        if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) done = (k == 2) ? launch_post_norm<T, 2, false>(ctx, lv, &lcv) : launch_post_norm<T, 1, false>(ctx, lv, &lcv);
+        else done = (k == 2) ? launch_post_norm<T, 4, true>(ctx, lv, &lcv) : launch_post_norm<T, 2, true>(ctx, lv, &lcv);
+        if (done) { ctx.post_norm_done = true; return; }
+    }
     if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) {
         if (k == 2) launch_stream<T, 2, MODE_POST, false>(ctx, lv, &lcv);
         else launch_stream<T, 1, MODE_POST, false>(ctx, lv, &lcv);
@@ -532,6 +566,7 @@ static bool fmg_entry_fused(Ctx& ctx, Level& lv, Level& lcv, int nu1)
 static int tail_top(const Ctx& ctx)
 {
     if (!(ctx.cfg.flags & MG_COARSE_TAIL)) return -1;
+    if (ctx.exact_coarse()) return -1;   // the coarsest level is a direct solve (coarse.cuh): every level runs its own kernels
     int top = std::min(kTailMaxLevel, ctx.cfg.finest_level);
     if (top < ctx.cfg.coarsest_level) return -1;
     if (ctx.L(top).distributed) return -1;

@@ -55,21 +55,25 @@ constexpr int kStreamWarps = 1;  // warps (independent work items) per CTA.  4 l
 #endif
 constexpr int ring_slots(int ns) { return ns >= MGB_DEEP_RING_MIN_NS ? 24 : 12; }
 
-template <typename T, int NS, int MODE>
+// NORM (POST only): one more pipeline stage computes the residual of the OUTPUT iterate and accumulates its sum of
+// squares (the convergence check of the tolerance loop, P:604-608 shape) -- no separate residual pass over the grid.
+template <typename T, int NS, int MODE, bool NORM = false>
 struct StreamCfg {
     static constexpr int V = Vec<T>::N;
     static constexpr bool HAS_POST = mode_has_post(MODE), HAS_PRE = mode_has_pre(MODE);
-    static constexpr int HL = NS + (HAS_PRE ? 2 : 0);                                   // columns needed to the left
-    static constexpr int HR = NS + (HAS_PRE ? 1 : 0) + (HAS_POST ? 1 : 0);              // ... to the right
+    static constexpr bool HAS_RES = HAS_PRE || NORM;                                    // residual stage after stage NS
+    static_assert(!(NORM && HAS_PRE), "NORM is a POST / SWEEPS option");
+    static constexpr int HL = NS + (HAS_PRE ? 2 : 0) + (NORM ? 1 : 0);                  // columns needed to the left
+    static constexpr int HR = NS + (HAS_RES ? 1 : 0) + (HAS_POST ? 1 : 0);              // ... to the right
     static constexpr int HMAX = HL > HR ? HL : HR;
     static constexpr int HLANES = (HMAX + V - 1) / V;                                   // halo lanes per side
     static constexpr int OUTW = 32 * V - 2 * V * HLANES;                                // output columns per strip
-    static constexpr int HT = NS + (HAS_PRE ? 2 : 0) + (HAS_POST ? 1 : 0);              // rows needed above
-    static constexpr int HB = NS + (HAS_PRE ? 2 : 0);                                   // rows needed below
+    static constexpr int HT = NS + (HAS_PRE ? 2 : 0) + (NORM ? 1 : 0) + (HAS_POST ? 1 : 0);   // rows needed above
+    static constexpr int HB = NS + (HAS_PRE ? 2 : 0) + (NORM ? 1 : 0);                  // rows needed below
     static constexpr int DEPTH = ring_slots(NS);
     static constexpr int NB = DEPTH / 3;                                                // ring blocks (power of two)
     static constexpr int D = DEPTH - NS - 3;                                            // prefetch distance (rows)
-    static constexpr int NW = NS + (HAS_PRE ? 1 : 0);                                   // register windows of u_s
+    static constexpr int NW = NS + (HAS_RES ? 1 : 0);                                   // register windows of u_s
     // slot: [u: 32 V][f: 32 V]; POST keeps the coarse rows in a second, half-rate ring
     static constexpr int SLOT_ELEMS = 32 * V * 2;
     static constexpr int CSLOT_ELEMS = 32 * (V / 2);
@@ -127,9 +131,9 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 // ZG ("zero guess"): the input iterate is known to be identically zero (first visit of a coarse level, P:613):
 // u is neither prefetched nor read, stage 0 is the constant 0.  Same arithmetic on the same values => same bits.
-template <typename T, int NS, int MODE, bool RBGS, bool ZG = false>
+template <typename T, int NS, int MODE, bool RBGS, bool ZG = false, bool NORM = false>
 struct Streamer {
-    typedef StreamCfg<T, NS, MODE> C;
+    typedef StreamCfg<T, NS, MODE, NORM> C;
     static constexpr int V = C::V;
     static constexpr int H = V / 2;
     static constexpr unsigned FULL = 0xffffffffu;
@@ -157,6 +161,7 @@ struct Streamer {
     T W[C::NW > 0 ? C::NW : 1][3][V];
     T WL[C::NW > 0 ? C::NW : 1][3], WR[C::NW > 0 ? C::NW : 1][3];
     T R[3][V], RL[3];  // PRE: residual window (left neighbours only)
+    double nacc;       // NORM: this lane's sum of squared residuals
 
     __device__ __forceinline__ Streamer(const StreamArgs<T>& a_) : a(a_) {}
 
@@ -325,6 +330,23 @@ struct Streamer {
             }
         }
 
+        // ---- NORM: residual of the output iterate u_NS (row y-NS-1), squared and accumulated on the stored points ----
+        if constexpr (NORM) {
+            const int rr = y - NS - 1;
+            if (!ring_row(rr) && lane_st && rr >= y0 && rr < y1) {
+                T ff[V];
+                ldv<T>(rslot<PH, NS + 1>() + 32 * V, ff);
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const T l = (k == 0) ? WL[NS][MID] : W[NS][MID][k - 1];
+                    const T r = (k == V - 1) ? WR[NS][MID] : W[NS][MID][k + 1];
+                    T o = resid_pt<T>(W[NS][MID][k], ff[k], sigma4<T>(W[NS][OLD][k], W[NS][NEW][k], l, r));
+                    mask_col(o, k);
+                    nacc += (double)o * (double)o;
+                }
+            }
+        }
+
         // ---- PRE: residual of u_NS (row y-NS-1) and full weighting (coarse row when that row is odd) ----
         if (C::HAS_PRE) {
             const int rr = y - NS - 1;
@@ -423,6 +445,7 @@ struct Streamer {
             for (int k = 0; k < V; ++k) R[p][k] = (T)0;
             RL[p] = (T)0;
         }
+        nacc = 0.0;
 
         g_u = a.u_in + (i64)ylo * a.pitch + c;
         g_f = a.f + (i64)ylo * a.pitch + c;
@@ -485,6 +508,23 @@ k_stream(const StreamArgs<T> a)
     const int item = blockIdx.x * kStreamWarps + warp;
     Streamer<T, NS, MODE, RBGS> st(a);
     st.run(reinterpret_cast<T*>(stream_smem), warp, threadIdx.x & 31, item);
+}
+
+// POST (or SWEEPS) with the residual norm of the output folded in: one partial sum of squares per work item (warp),
+// reduced by warp shuffles in a fixed order; k_sum_partials adds the partials in index order
+template <typename T, int NS, int MODE, bool RBGS>
+__global__ void __launch_bounds__(kStreamWarps * 32, kStreamMinCtas / kStreamWarps)
+k_stream_norm(const StreamArgs<T> a, double* __restrict__ partials)
+{
+    extern __shared__ __align__(16) unsigned char stream_smem[];
+    const int warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * kStreamWarps + warp;
+    Streamer<T, NS, MODE, RBGS, false, true> st(a);
+    st.run(reinterpret_cast<T*>(stream_smem), warp, threadIdx.x & 31, item);
+    double acc = st.nacc;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, s);
+    if ((threadIdx.x & 31) == 0) partials[item] = acc;
 }
 
 // POSTPRE (visit chains, opt-in MGB200_CHAIN=1) needs ~142 registers at NS = 4: its own entry point with a launch bound

@@ -34,10 +34,11 @@ __host__ __device__ constexpr int tail_off(int L)
     return off;
 }
 
+// arrays of levels 1..top, and one word after the arrays of ALL tail levels (warp 0 hands its buffer parities back there)
 template <typename T>
-inline size_t tail_smem_bytes(int top, int /*coarsest*/)
+inline size_t tail_smem_bytes(int /*top*/, int /*coarsest*/)
 {
-    return (size_t)tail_off(top + 1) * sizeof(T) + 16;
+    return (size_t)tail_off(kTailMaxLevel + 1) * sizeof(T) + 16;
 }
 
 template <typename T, int L>
@@ -45,6 +46,7 @@ struct TailLv {
     static constexpr int N = 1 << L, P = N + 1, SZ = P * P;
     static constexpr int YIT = (N - 1 + kTailWarps - 1) / kTailWarps;   // row iterations per warp
     static constexpr int XIT = (N - 1 + 31) / 32;                       // column iterations per lane
+    static constexpr int WIT = ((N - 1) * (N - 1) + 31) / 32;           // point iterations per lane in single-warp mode
     T* buf;      // [u ping][u pong / residual scratch][f]
     __device__ __forceinline__ TailLv(T* base) : buf(base + tail_off(L)) {}
     __device__ __forceinline__ T* A(unsigned cur) const { return buf + (((cur >> L) & 1u) ? SZ : 0); }
@@ -52,13 +54,28 @@ struct TailLv {
     __device__ __forceinline__ T* F() const { return buf + 2 * SZ; }
 };
 
-#define MG_TAIL_FOR_POINTS(LV)                                            \
-    _Pragma("unroll") for (int it_ = 0; it_ < LV::YIT; ++it_)             \
-    _Pragma("unroll") for (int h_ = 0; h_ < LV::XIT; ++h_)                \
-        if (const int y = 1 + warp + it_ * kTailWarps; y < LV::N)         \
-            if (const int x = 1 + lane + 32 * h_; x < LV::N)
+// Levels <= kTailWarpLevel are run by WARP 0 ALONE with __syncwarp() between the phases: a phase on a 15^2 (or smaller)
+// grid is a few instructions per lane, and a 1024-thread block barrier costs more than the phase itself (ncu, round 2:
+// barrier + instruction-fetch stalls dominate k_tail; a W-cycle visits these levels 44 times per tail launch).  The other
+// 31 warps wait at one block barrier for the whole sub-cycle.  Same arrays, same formulas, same bits.
+#ifndef MGB_TAIL_WARP_LEVEL
+#define MGB_TAIL_WARP_LEVEL 4
+#endif
+constexpr int kTailWarpLevel = MGB_TAIL_WARP_LEVEL;
 
-template <typename T, bool RBGS, int L>
+template <bool WARP> __device__ __forceinline__ void tail_sync()
+{
+    if constexpr (WARP) __syncwarp();
+    else __syncthreads();
+}
+
+// the interior points of level LV, spread over the whole block (one row per warp) or over the lanes of warp 0
+#define MG_TAIL_FOR_POINTS(LV, WARP)                                                                      \
+    _Pragma("unroll") for (int it_ = 0; it_ < ((WARP) ? LV::WIT : LV::YIT * LV::XIT); ++it_)              \
+        if (const int y = (WARP) ? 1 + (lane + 32 * it_) / (LV::N - 1) : 1 + warp + (it_ / LV::XIT) * kTailWarps; y < LV::N)   \
+            if (const int x = (WARP) ? 1 + (lane + 32 * it_) % (LV::N - 1) : 1 + lane + 32 * (it_ % LV::XIT); x < LV::N)
+
+template <typename T, bool RBGS, int L, bool WARP>
 __device__ __forceinline__ void tail_smooth(T* base, const TailArgs<T>& a, unsigned& cur, int nu, int warp, int lane)
 {
     typedef TailLv<T, L> LV;
@@ -69,38 +86,40 @@ __device__ __forceinline__ void tail_smooth(T* base, const TailArgs<T>& a, unsig
         if (!RBGS) {
             const T* src = lv.A(cur);
             T* dst = lv.B(cur);
-            MG_TAIL_FOR_POINTS(LV)
+            MG_TAIL_FOR_POINTS(LV, WARP)
             {
                 const int i = y * P + x;
                 dst[i] = jacobi_pt<T>(a.c0, a.c1, src[i], F[i], sigma4<T>(src[i - P], src[i + P], src[i - 1], src[i + 1]));
             }
-            __syncthreads();
+            tail_sync<WARP>();
             cur ^= (1u << L);
         } else {
             T* p = lv.A(cur);
 #pragma unroll
             for (int colour = 0; colour < 2; ++colour) {
-                MG_TAIL_FOR_POINTS(LV)
+                MG_TAIL_FOR_POINTS(LV, WARP)
                 {
                     if (((y + x) & 1) == colour) {
                         const int i = y * P + x;
                         p[i] = gs_pt<T>(F[i], sigma4<T>(p[i - P], p[i + P], p[i - 1], p[i + 1]));
                     }
                 }
-                __syncthreads();
+                tail_sync<WARP>();
             }
         }
     }
 }
 
 // one cycle visit of level L (vcyclemultigrid P:575-627)
-template <typename T, bool RBGS, int L>
-__device__ __noinline__ void tail_visit(T* base, const TailArgs<T>& a, unsigned& cur, int warp, int lane)
+// Inlined at its single call site per level (the recursion is a template recursion), so `cur` and the arguments live in
+// registers: as a __noinline__ function taking `cur` by reference every use of it was a local-memory round trip.
+template <typename T, bool RBGS, int L, bool WARP>
+__device__ __forceinline__ void tail_visit(T* base, const TailArgs<T>& a, unsigned& cur, int warp, int lane)
 {
     typedef TailLv<T, L> LV;
-    tail_smooth<T, RBGS, L>(base, a, cur, a.nu1, warp, lane);                 // P:581
+    tail_smooth<T, RBGS, L, WARP>(base, a, cur, a.nu1, warp, lane);           // P:581
     if (L <= a.coarsest) {
-        tail_smooth<T, RBGS, L>(base, a, cur, a.nu2, warp, lane);             // P:585
+        tail_smooth<T, RBGS, L, WARP>(base, a, cur, a.nu2, warp, lane);       // P:585
         return;
     }
     if constexpr (L > 1) {
@@ -112,30 +131,41 @@ __device__ __noinline__ void tail_visit(T* base, const TailArgs<T>& a, unsigned&
             const T* u = lv.A(cur);
             const T* F = lv.F();
             T* r = lv.B(cur);
-            MG_TAIL_FOR_POINTS(LV)
+            MG_TAIL_FOR_POINTS(LV, WARP)
             {
                 const int i = y * P + x;
                 r[i] = resid_pt<T>(u[i], F[i], sigma4<T>(u[i - P], u[i + P], u[i - 1], u[i + 1]));
             }
-            __syncthreads();
+            tail_sync<WARP>();
             cur &= ~(1u << (L - 1));
             T* fc = lc.F();
             T* uc = lc.A(cur);
-            MG_TAIL_FOR_POINTS(LC)
+            MG_TAIL_FOR_POINTS(LC, WARP)
             {
                 const int i = (2 * y) * P + 2 * x;
                 fc[y * Pc + x] = fw_pt<T>(a.w, r[i - P - 1], r[i - P + 1], r[i + P - 1], r[i + P + 1],
                                           r[i - 1], r[i + 1], r[i - P], r[i + P], r[i]);
                 uc[y * Pc + x] = (T)0;
             }
-            __syncthreads();
+            tail_sync<WARP>();
         }
         const int reps = (L - 1 <= a.coarsest) ? 1 : (a.gamma < 1 ? 1 : a.gamma);
-        for (int g = 0; g < reps; ++g) tail_visit<T, RBGS, L - 1>(base, a, cur, warp, lane);   // P:617
+        if constexpr (!WARP && L - 1 <= kTailWarpLevel) {
+            // hand the sub-cycle of the small levels to warp 0; its buffer parities come back through shared memory
+            unsigned* cur_slot = reinterpret_cast<unsigned*>(base + tail_off(kTailMaxLevel + 1));
+            if (warp == 0) {
+                for (int g = 0; g < reps; ++g) tail_visit<T, RBGS, L - 1, true>(base, a, cur, warp, lane);   // P:617
+                if (lane == 0) *cur_slot = cur;
+            }
+            __syncthreads();
+            cur = *cur_slot;
+        } else {
+            for (int g = 0; g < reps; ++g) tail_visit<T, RBGS, L - 1, WARP>(base, a, cur, warp, lane);       // P:617
+        }
         {   // prolongation + correction (P:620-624)
             const T* e = lc.A(cur);
             T* u = lv.A(cur);
-            MG_TAIL_FOR_POINTS(LV)
+            MG_TAIL_FOR_POINTS(LV, WARP)
             {
                 const T* c = e + (y >> 1) * Pc + (x >> 1);
                 T v;
@@ -145,9 +175,9 @@ __device__ __noinline__ void tail_visit(T* base, const TailArgs<T>& a, unsigned&
                 else v = (T)0.25 * (((c[0] + c[Pc]) + c[1]) + c[Pc + 1]);                         // P:419
                 u[y * P + x] = u[y * P + x] + v;                                                  // P:623
             }
-            __syncthreads();
+            tail_sync<WARP>();
         }
-        tail_smooth<T, RBGS, L>(base, a, cur, a.nu2, warp, lane);             // P:625
+        tail_smooth<T, RBGS, L, WARP>(base, a, cur, a.nu2, warp, lane);       // P:625
     }
 }
 
@@ -183,15 +213,25 @@ __device__ __forceinline__ void tail_run(T* base, const TailArgs<T>& a, int warp
             }
     }
     __syncthreads();
-    tail_visit<T, RBGS, TOP>(base, a, cur, warp, lane);
+    if constexpr (TOP <= kTailWarpLevel) {      // the whole problem is a small level: warp 0 runs it alone
+        unsigned* cur_slot = reinterpret_cast<unsigned*>(base + tail_off(kTailMaxLevel + 1));
+        if (warp == 0) {
+            tail_visit<T, RBGS, TOP, true>(base, a, cur, warp, lane);
+            if (lane == 0) *cur_slot = cur;
+        }
+        __syncthreads();
+        cur = *cur_slot;
+    } else {
+        tail_visit<T, RBGS, TOP, false>(base, a, cur, warp, lane);
+    }
     {
         const T* A = lv.A(cur);
-        MG_TAIL_FOR_POINTS(LV) { a.u[(i64)y * a.pitch + x] = A[y * P + x]; }
+        MG_TAIL_FOR_POINTS(LV, false) { a.u[(i64)y * a.pitch + x] = A[y * P + x]; }
     }
 }
 
 template <typename T, bool RBGS>
-__global__ void __launch_bounds__(kTailThreads)
+__global__ void __launch_bounds__(kTailThreads, 1)   // one CTA per SM: 64 registers per thread (the default heuristic caps at 32 and spills)
 k_tail(const TailArgs<T> a)
 {
     extern __shared__ __align__(16) unsigned char tail_smem[];
@@ -213,7 +253,7 @@ k_tail(const TailArgs<T> a)
 // zero-guess variant (opt-in, MGB200_ZERO_GUESS=1): u of the top level is known to be zero and is not read.
 // A separate kernel so that k_tail stays byte-identical to the GPU-verified build.
 template <typename T, bool RBGS>
-__global__ void __launch_bounds__(kTailThreads)
+__global__ void __launch_bounds__(kTailThreads, 1)   // one CTA per SM: 64 registers per thread (the default heuristic caps at 32 and spills)
 k_tail_zg(const TailArgs<T> a)
 {
     extern __shared__ __align__(16) unsigned char tail_smem[];

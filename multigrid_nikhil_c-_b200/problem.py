@@ -8,8 +8,9 @@
 * `ProblemVar` / `multigrid_solver`  the call shape of the reference's second sketch (Multigrid_functions.cpp,
   "M:line"): one problem object carrying a per-level right-hand-side dictionary `b_dict` (M:16-26), solved by
   `multigrid_solver(obj)` = full multigrid from the coarsest level up (M:175-197), here over the structured-grid
-  operators of libmgb200 (the unstructured-mesh transfer operators M:98-130 and the Eigen SparseLU coarse solve
-  M:63-72 are out of scope; the coarsest level is smoothed as in P:583-587).
+  operators of libmgb200 (the unstructured-mesh transfer operators M:98-130 are out of scope).
+  Like the sketch, the coarsest level is solved directly (`direct_solver`, M:63-72 / M:136-139: coarse_solver="exact");
+  coarse_solver="sweeps" gives the first version's nu1+nu2 sweeps there (P:583-587).
 
 This is set-up code: it builds host vectors and sequences C-ABI calls.  The solver arithmetic (smoothing, residual,
 transfers, cycles) runs in libmgb200.so on the GPU.
@@ -65,6 +66,7 @@ class ProblemVar:
     mu2: int = 1                     # M:48
     omega: float = 2.0 / 3.0         # M:49 reads `4 / 5`, an integer division that evaluates to 0 (erratum); P:127 value
     smoother: str = "jacobi"
+    coarse_solver: str = "exact"     # M:136-139: direct solve on the coarsest level ("sweeps": P:583-587)
     dtype: type = np.float64
     b_dict: Dict[int, np.ndarray] = field(default_factory=dict)
 
@@ -82,7 +84,7 @@ def fullmultigrid(mg: Multigrid, obj: ProblemVar, level: Optional[int] = None) -
             mg.restrict_rhs(l + 1)
     mg.zero_u(obj.coarsest_level)                          # M:176
     for _ in range(obj.mu0 + 1):
-        mg.cycle(obj.coarsest_level, obj.mu1, obj.mu2, 1)  # coarsest level: nu1 + nu2 sweeps (P:583-587)
+        mg.cycle(obj.coarsest_level, obj.mu1, obj.mu2, 1)  # coarsest level: direct solve (M:137) or nu1 + nu2 sweeps (P:583-587)
     for l in range(obj.coarsest_level + 1, top + 1):
         mg.prolong_set(l)                                  # M:185
         for _ in range(obj.mu0 + 1):                       # M:186-188
@@ -93,5 +95,5 @@ def fullmultigrid(mg: Multigrid, obj: ProblemVar, level: Optional[int] = None) -
 def multigrid_solver(obj: ProblemVar, **ctx_kw) -> np.ndarray:
     """M:193-197: create the execution context, run full multigrid on the finest level's load vector."""
     with Multigrid(obj.finest_level, coarsest_level=obj.coarsest_level, dtype=obj.dtype, smoother=obj.smoother,
-                   omega=obj.omega, **ctx_kw) as mg:
+                   omega=obj.omega, coarse_solver=obj.coarse_solver, **ctx_kw) as mg:
         return fullmultigrid(mg, obj)

@@ -33,7 +33,7 @@ class Multigrid:
                  smoother: str = "jacobi", omega: float = 2.0 / 3.0, restrict_weight: float = 0.25,
                  device: int = -1, graph: bool = True, fused: bool = True, coarse_tail: bool = True,
                  rank: int = 0, world: int = 1, agglomerate_level: int = 0,
-                 comm_id: Optional[bytes] = None):
+                 comm_id: Optional[bytes] = None, coarse_solver: str = "sweeps"):
         self._lib = capi.lib()
         self._ctx = ctypes.c_void_p()
         self.dtype = np.dtype(dtype)
@@ -52,6 +52,8 @@ class Multigrid:
                     (capi.MG_COARSE_TAIL if coarse_tail else 0)
         cfg.rank, cfg.world = rank, world
         cfg.agglomerate_level = agglomerate_level
+        # "sweeps": nu1+nu2 sweeps on the coarsest level (P:583-587); "exact": direct solve there (direct_solver, M:63-72)
+        cfg.coarse_solver = {"sweeps": capi.MG_COARSE_SWEEPS, "exact": capi.MG_COARSE_EXACT}[coarse_solver]
         self._comm_id = None
         if comm_id is not None:
             self._comm_id = ctypes.create_string_buffer(bytes(comm_id), capi.MG_COMM_ID_BYTES)

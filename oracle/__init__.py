@@ -33,7 +33,7 @@ def build(native: bool = False, quiet: bool = True) -> str:
 class _Params(ctypes.Structure):
     _fields_ = [("coarsest_level", ctypes.c_int), ("nu1", ctypes.c_int), ("nu2", ctypes.c_int),
                 ("gamma", ctypes.c_int), ("smoother", ctypes.c_int), ("omega", ctypes.c_double),
-                ("restrict_weight", ctypes.c_double), ("nthreads", ctypes.c_int)]
+                ("restrict_weight", ctypes.c_double), ("nthreads", ctypes.c_int), ("coarse_exact", ctypes.c_int)]
 
 
 @dataclass
@@ -46,10 +46,11 @@ class Params:
     omega: float = 2.0 / 3.0   # P:127
     restrict_weight: float = 0.25
     nthreads: int = 1
+    coarse_exact: int = 0      # 1: exact solve on the coarsest level (M:63-72) instead of nu1+nu2 sweeps (P:583-587)
 
     def c(self) -> _Params:
         return _Params(self.coarsest_level, self.nu1, self.nu2, self.gamma, self.smoother,
-                       self.omega, self.restrict_weight, self.nthreads)
+                       self.omega, self.restrict_weight, self.nthreads, self.coarse_exact)
 
 
 _SUF = {np.dtype(np.float64): "_f64", np.dtype(np.float32): "_f32"}
@@ -169,6 +170,13 @@ class Oracle:
         out = np.array(vec_h, copy=True)
         self._chk(out, vec_2h)
         self._f("mgo_prolong_correct", out)(_ptr(vec_2h), _side(vec_2h), _ptr(out), int(nthreads))
+        return out
+
+    def coarse_exact(self, f_h):
+        """Exact solve A u = f on one level (direct_solver, M:63-72): sine-transform diagonalisation, see the .inc."""
+        f_h = np.ascontiguousarray(f_h)
+        out = np.zeros_like(f_h)
+        self._f("mgo_coarse_exact", out)(_ptr(out), _ptr(f_h), _side(out))
         return out
 
     def globalforcefunction(self, level, f=4.0, dtype=np.float64):

@@ -1,5 +1,6 @@
 /* oracle/mg_oracle.c — TEST INFRASTRUCTURE, NOT PRODUCT CODE (see mg_oracle.h).
  * Build: gcc -O3 -ffp-contract=off -fopenmp -fPIC -shared (oracle/Makefile). */
+#define _GNU_SOURCE   /* M_PI */
 #include "mg_oracle.h"
 
 #include <math.h>
@@ -19,6 +20,7 @@ void mgo_params_default(mgo_params* p)
     p->omega = 2.0 / 3.0; /* P:127 */
     p->restrict_weight = 0.25;
     p->nthreads = 1;
+    p->coarse_exact = 0;
 }
 
 int mgo_max_threads(void)

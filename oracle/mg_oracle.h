@@ -39,6 +39,8 @@ typedef struct {
     double omega;           /* P:127, 2/3                                                  */
     double restrict_weight; /* 0.25 intended (E2+E4 repaired); 1/16 literal FD weight      */
     int nthreads;           /* OpenMP threads used by every loop                           */
+    int coarse_exact;       /* 0: coarsest level = nu1+nu2 sweeps (P:583-587); 1: exact solve, no
+                               smoothing there (direct_solver, Multigrid_functions.cpp M:63-72 / M:136-139) */
 } mgo_params;
 
 void mgo_params_default(mgo_params* p);
@@ -55,6 +57,7 @@ int mgo_max_threads(void);
     void mgo_interpolation2d##S(const T* vec_2h, int m, T* vec_h, int nthreads);                     \
     void mgo_prolong_correct##S(const T* vec_2h, int m, T* vec_h, int nthreads);                     \
     void mgo_globalforcefunction##S(T* out, int level, double f);                                    \
+    void mgo_coarse_exact##S(T* u, const T* f, int n);                                               \
     void mgo_vcyclemultigrid##S(T* vec_h, const T* f_h, int level, const mgo_params* p);             \
     void mgo_fullmultigrid##S(T* vec_h, const T* f_h, int level, int cycles, const mgo_params* p);   \
     int mgo_solve##S(T* vec_h, const T* f_h, int level, double rtol, int max_cycles,                 \

@@ -184,3 +184,37 @@ def test_golden_fixtures_if_present(orc):
                "vcycle": lambda: orc.vcyclemultigrid(x, b, p),
                "fmg": lambda: orc.fullmultigrid(b, 1, p)}[case["op"]]()
         assert np.array_equal(got, g[name]), name
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-3)])
+@pytest.mark.parametrize("level", [1, 2, 4, 6])
+def test_exact_coarse_solve_solves_the_five_point_system(orc, level, dtype, tol):
+    """mgo_coarse_exact (direct_solver, M:63-72): A u = f to rounding, and A^-1 of the constant load is symmetric."""
+    n = (1 << level) - 1
+    f = np.random.default_rng(level).uniform(-1, 1, n * n).astype(dtype)
+    u = orc.coarse_exact(f)
+    assert np.abs(orc.residual(u, f)).max() <= tol * max(1.0, float(np.abs(f).max()))
+    c = orc.coarse_exact(np.ones(n * n, dtype=dtype)).reshape(n, n)
+    assert np.allclose(c, c.T, rtol=0, atol=tol) and np.allclose(c, c[::-1, ::-1], rtol=0, atol=tol)
+    if level == 1:
+        assert orc.coarse_exact(np.array([1.0], dtype=dtype))[0] == pytest.approx(0.25, rel=1e-6)
+
+
+def test_exact_coarse_solve_fixes_the_reference_depth(orc):
+    """coarsest = finest - 3 (P:17-18): sweeps on the coarsest grid stall (factor ~0.97), the exact solve of the
+    second version (M:136-139) gives the textbook V(2,2) factor, the same as coarsening down to one unknown."""
+    import oracle
+    level = 8
+    n = (1 << level) - 1
+    b = np.full(n * n, 4.0 / (1 << level) ** 2)
+    fac = {}
+    for name, p in (("sweeps", oracle.Params(coarsest_level=5, nthreads=4)),
+                    ("exact", oracle.Params(coarsest_level=5, nthreads=4, coarse_exact=1)),
+                    ("deep", oracle.Params(coarsest_level=1, nthreads=4))):
+        u = np.zeros(n * n)
+        h = [orc.norm2(orc.residual(u, b))]
+        for _ in range(8):
+            u = orc.vcyclemultigrid(u, b, p)
+            h.append(orc.norm2(orc.residual(u, b)))
+        fac[name] = h[-1] / h[-2]
+    assert fac["sweeps"] > 0.9 and 0.18 < fac["exact"] < 0.25 and abs(fac["exact"] - fac["deep"]) < 0.03, fac

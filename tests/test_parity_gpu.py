@@ -302,6 +302,53 @@ def test_synthetic_rhs_and_checksum_match_their_numpy_restatements(mgb, level, d
         assert mg.checksum(level, 0) != synth_ref.checksum(level, x)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("smoother,gamma", [("jacobi", 1), ("rbgs", 1), ("jacobi", 2)])
+@pytest.mark.parametrize("level,coarsest", [(3, 3), (5, 2), (7, 4), (8, 5), (9, 6)])
+def test_exact_coarsest_solve_cycles_bitwise(mgb, orc, level, coarsest, dtype, smoother, gamma):
+    """MG_COARSE_EXACT (direct_solver, M:63-72, called at M:136-139): the coarsest level is solved directly (sine-transform
+    diagonalisation, csrc/coarse.cuh) instead of nu1+nu2 sweeps (P:583-587).  Cycles, full multigrid and the host call on
+    the coarsest level alone equal the oracle bit for bit, with and without CUDA graphs."""
+    x, b = rand_vec(level, dtype, 91), rand_vec(level, dtype, 92, 1e-3)
+    p = oracle.Params(coarsest_level=coarsest, gamma=gamma, smoother=1 if smoother == "rbgs" else 0, nthreads=4, coarse_exact=1)
+    want = [x]
+    for _ in range(2):
+        want.append(orc.vcyclemultigrid(want[-1], b, p))
+    for graph in (False, True):
+        with mgb.Multigrid(level, coarsest_level=coarsest, dtype=dtype, smoother=smoother, graph=graph, coarse_solver="exact") as mg:
+            mg.set_u(level, x)
+            mg.set_rhs(level, b)
+            for k in range(2):
+                mg.cycle(level, 2, 2, gamma)
+                assert_bitwise(mg.get_u(level), want[k + 1], f"exact-coarse cycle {k + 1} graph={graph}")
+            pv = oracle.Params(coarsest_level=coarsest, smoother=p.smoother, nthreads=4, coarse_exact=1)
+            assert_bitwise(mg.fullmultigrid(b, 1, 2, 2), orc.fullmultigrid(b, 1, pv), "fmg with exact coarse solve")
+            bc = rand_vec(coarsest, dtype, 93)
+            got = mg.vcyclemultigrid(np.zeros_like(bc), bc, 2, 2, 1)          # a cycle ON the coarsest level = the solve
+            assert_bitwise(got, orc.coarse_exact(bc), "direct solve on the coarsest level")
+
+
+def test_exact_coarsest_solve_restores_the_textbook_rate_at_the_reference_depth(mgb, orc):
+    """The reference coarsens only three levels (coarsest = finest - 3, P:17-18).  With sweeps on that coarsest grid the
+    V(2,2) factor is ~0.9-0.98; with the exact solve of its second version it is the textbook ~0.22."""
+    level, coarsest = 9, 6
+    hist = {}
+    for cs in ("sweeps", "exact"):
+        with mgb.Multigrid(level, coarsest_level=coarsest, coarse_solver=cs) as mg:
+            mg.force_constant(4.0)
+            mg.zero_u(level)
+            k, rel, h = mg.solve(1e-8, 12)
+            hist[cs] = h
+    f_sweeps = hist["sweeps"][-1] / hist["sweeps"][-2]
+    f_exact = hist["exact"][-1] / hist["exact"][-2]
+    assert f_sweeps > 0.85 and 0.15 < f_exact < 0.26, (f_sweeps, f_exact)
+    with mgb.Multigrid(level, coarsest_level=1) as mg:      # coarsening all the way down gives the same rate
+        mg.force_constant(4.0)
+        mg.zero_u(level)
+        _, _, h1 = mg.solve(1e-8, 12)
+    assert abs(h1[-1] / h1[-2] - f_exact) < 0.05
+
+
 def test_golden_fixtures(mgb):
     """Committed oracle outputs (tests/golden/oracle_golden.npz, made by make_golden.py)."""
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.npz"))

@@ -50,13 +50,15 @@ def _oracle_v2(orc, obj, p):
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("smoother", ["jacobi", "rbgs"])
-def test_multigrid_solver_v2_shape_bitwise(mgb, orc, dtype, smoother):
+@pytest.mark.parametrize("coarse", ["exact", "sweeps"])
+def test_multigrid_solver_v2_shape_bitwise(mgb, orc, dtype, smoother, coarse):
     """multigrid_solver(ProblemVar): per-level load vectors where given (M:183), restricted ones elsewhere (P:641)."""
     top = 7
-    obj = mgb.ProblemVar(finest_level=top, coarsest_level=2, mu0=2, mu1=1, mu2=1, smoother=smoother, dtype=dtype)
+    obj = mgb.ProblemVar(finest_level=top, coarsest_level=2, mu0=2, mu1=1, mu2=1, smoother=smoother, dtype=dtype, coarse_solver=coarse)
     obj.b_dict[top] = rand_vec(top, dtype, 61, 1e-3)
     obj.b_dict[top - 2] = rand_vec(top - 2, dtype, 62, 1e-3)         # an independently assembled coarse load vector
-    p = oracle.Params(coarsest_level=2, nu1=1, nu2=1, smoother=1 if smoother == "rbgs" else 0, nthreads=2)
+    p = oracle.Params(coarsest_level=2, nu1=1, nu2=1, smoother=1 if smoother == "rbgs" else 0, nthreads=2,
+                      coarse_exact=1 if coarse == "exact" else 0)
     assert_bitwise(mgb.multigrid_solver(obj), _oracle_v2(orc, obj, p), "multigrid_solver")
 
 
