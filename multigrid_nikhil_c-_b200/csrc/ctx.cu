@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "coarse.cuh"
 #include "comm.cuh"
@@ -217,6 +218,18 @@ void Ctx::release() noexcept
     for (auto& lv : levels)
         for (int k = 0; k < 4; ++k)
             if (lv.alloc[k]) cudaFree(lv.alloc[k]);
+    {   // (every handle is checked: a failed stager_init leaves some of them null)
+        for (int t = 0; t < Stager::kThreads; ++t) {
+            if (stager.st[t]) { cudaStreamSynchronize(stager.st[t]); cudaStreamDestroy(stager.st[t]); }
+            if (stager.ev_done[t]) cudaEventDestroy(stager.ev_done[t]);
+            for (int b = 0; b < Stager::kBufs; ++b) {
+                if (stager.pinned[t][b]) cudaFreeHost(stager.pinned[t][b]);
+                if (stager.ev[t][b]) cudaEventDestroy(stager.ev[t][b]);
+            }
+        }
+        if (stager.ev_main) cudaEventDestroy(stager.ev_main);
+        stager = Stager();
+    }
     if (d_partials) cudaFree(d_partials);
     if (d_dst_S) cudaFree(d_dst_S);
     if (d_dst_d) cudaFree(d_dst_d);
@@ -320,6 +333,93 @@ static char* which_ptr(Level& lv, Ctx::Which w)
     }
 }
 
+void Ctx::stager_init()
+{
+    if (stager.ready) return;
+    for (int t = 0; t < Stager::kThreads; ++t) {
+        MG_CK(cudaStreamCreateWithFlags(&stager.st[t], cudaStreamNonBlocking));
+        MG_CK(cudaEventCreateWithFlags(&stager.ev_done[t], cudaEventDisableTiming));
+        for (int b = 0; b < Stager::kBufs; ++b) {
+            MG_CK(cudaMallocHost((void**)&stager.pinned[t][b], Stager::kChunkBytes));
+            MG_CK(cudaEventCreateWithFlags(&stager.ev[t][b], cudaEventDisableTiming));
+        }
+    }
+    MG_CK(cudaEventCreateWithFlags(&stager.ev_main, cudaEventDisableTiming));
+    stager.ready = true;
+}
+
+void Ctx::copy_rows_staged(char* dev, size_t dpitch, char* host, size_t row_bytes, int rows, bool to_device)
+{
+    stager_init();
+    const int rows_per_chunk = (int)std::max<size_t>(1, Stager::kChunkBytes / row_bytes);
+    const int nchunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
+    // the worker streams start after everything already queued on the context's stream (which may still use the array)
+    MG_CK(cudaEventRecord(stager.ev_main, stream));
+    cudaError_t errs[Stager::kThreads];
+    auto work = [&](int t) {
+        cudaError_t e = cudaSetDevice(device);
+        cudaStream_t st = stager.st[t];
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, stager.ev_main, 0);
+        int k = 0;
+        int pend_c = -1, pend_b = -1;   // device -> host: the chunk whose copy into a pinned buffer is in flight
+        auto drain = [&]() {
+            if (pend_c < 0 || e != cudaSuccess) return;
+            e = cudaEventSynchronize(stager.ev[t][pend_b]);
+            const int r0 = pend_c * rows_per_chunk, nr = std::min(rows_per_chunk, rows - r0);
+            if (e == cudaSuccess) std::memcpy(host + (size_t)r0 * row_bytes, stager.pinned[t][pend_b], (size_t)nr * row_bytes);
+            pend_c = -1;
+        };
+        for (int c = t; c < nchunks && e == cudaSuccess; c += Stager::kThreads, ++k) {
+            const int b = k % Stager::kBufs;
+            const int r0 = c * rows_per_chunk, nr = std::min(rows_per_chunk, rows - r0);
+            char* pin = stager.pinned[t][b];
+            if (to_device) {
+                e = cudaEventSynchronize(stager.ev[t][b]);      // the previous copy out of this buffer has finished
+                if (e != cudaSuccess) break;
+                std::memcpy(pin, host + (size_t)r0 * row_bytes, (size_t)nr * row_bytes);
+                e = cudaMemcpy2DAsync(dev + (size_t)r0 * dpitch, dpitch, pin, row_bytes, row_bytes, (size_t)nr, cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaEventRecord(stager.ev[t][b], st);
+            } else {
+                e = cudaMemcpy2DAsync(pin, row_bytes, dev + (size_t)r0 * dpitch, dpitch, row_bytes, (size_t)nr, cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaEventRecord(stager.ev[t][b], st);
+                drain();                                         // the previous chunk, while this one is in flight
+                pend_c = c;
+                pend_b = b;
+            }
+        }
+        drain();
+        if (e == cudaSuccess) e = cudaEventRecord(stager.ev_done[t], st);
+        errs[t] = e;
+    };
+    std::thread th[Stager::kThreads];
+    for (int t = 1; t < Stager::kThreads; ++t) th[t] = std::thread(work, t);
+    work(0);
+    for (int t = 1; t < Stager::kThreads; ++t) th[t].join();
+    for (int t = 0; t < Stager::kThreads; ++t) MG_CK(errs[t]);
+    for (int t = 0; t < Stager::kThreads; ++t) MG_CK(cudaStreamWaitEvent(stream, stager.ev_done[t], 0));
+}
+
+// pinned (or registered / managed) host memory goes straight through the copy engine; ordinary pageable memory -- what
+// a std::vector or a numpy array is -- through the staged multi-thread path when the transfer is large enough to matter
+void Ctx::copy_rows(char* dev, size_t dpitch, char* host, size_t row_bytes, int rows, bool to_device)
+{
+    if (rows <= 0) return;
+    bool pageable = false;
+#ifndef MGB_EMU
+    if ((size_t)rows * row_bytes >= Stager::kMinBytes) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, host) == cudaSuccess) pageable = (at.type == cudaMemoryTypeUnregistered);
+        else cudaGetLastError();
+    }
+#endif
+    if (pageable) {
+        copy_rows_staged(dev, dpitch, host, row_bytes, rows, to_device);
+        return;
+    }
+    if (to_device) MG_CK(cudaMemcpy2DAsync(dev, dpitch, host, row_bytes, row_bytes, (size_t)rows, cudaMemcpyHostToDevice, stream));
+    else MG_CK(cudaMemcpy2DAsync(host, row_bytes, dev, dpitch, row_bytes, (size_t)rows, cudaMemcpyDeviceToHost, stream));
+}
+
 void Ctx::set_host(int level, Which w, const void* host)
 {
     MG_REQUIRE(host != nullptr, "null host pointer");
@@ -329,8 +429,7 @@ void Ctx::set_host(int level, Which w, const void* host)
     const int ya = std::max(lv.st_lo, 1), yb = std::min(lv.st_hi, lv.N);
     char* dst = which_ptr(lv, w) + ((i64)ya * lv.pitch + 1) * esize;
     const char* src = (const char*)host + (i64)(ya - 1) * n * esize;
-    MG_CK(cudaMemcpy2DAsync(dst, (size_t)lv.pitch * esize, src, (size_t)n * esize, (size_t)n * esize,
-                            (size_t)(yb - ya), cudaMemcpyHostToDevice, stream));
+    copy_rows(dst, (size_t)lv.pitch * esize, const_cast<char*>(src), (size_t)n * esize, yb - ya, true);
     MG_CK(cudaStreamSynchronize(stream));
     set_halo(lv, w, lv.halo);
 }
@@ -344,8 +443,7 @@ void Ctx::get_host(int level, Which w, void* host)
     const int ya = lv.own_lo, yb = lv.own_hi;
     const char* src = which_ptr(lv, w) + ((i64)ya * lv.pitch + 1) * esize;
     char* dst = (char*)host + (i64)(ya - 1) * n * esize;
-    MG_CK(cudaMemcpy2DAsync(dst, (size_t)n * esize, src, (size_t)lv.pitch * esize, (size_t)n * esize,
-                            (size_t)(yb - ya), cudaMemcpyDeviceToHost, stream));
+    copy_rows(const_cast<char*>(src), (size_t)lv.pitch * esize, dst, (size_t)n * esize, yb - ya, false);
     MG_CK(cudaStreamSynchronize(stream));
 }
 
@@ -422,7 +520,7 @@ void Ctx::smooth_t(int level, int nu)
             lv.hv_u = 0;
             ++s;
         }
-    } else {
+    } else if (!fused_rbgs(*this, lv, nu)) {
         for (int s = 0; s < nu; ++s)
             for (int colour = 0; colour < 2; ++colour) {
                 ensure_halo(lv, W_U, 1);

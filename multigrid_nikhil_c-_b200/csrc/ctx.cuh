@@ -106,6 +106,20 @@ struct FusedKnobs {
     int force_ry_minN = 4096;
 };
 
+// Staging of PAGEABLE host vectors (the std::vector call shape of include/mgb200_driver.hpp): a cudaMemcpy from pageable
+// memory is copied through a driver bounce buffer by one thread; here a few host threads copy row chunks through the
+// context's own pinned buffers on their own streams, so the copy engines stay busy.  Pinned callers skip all of this.
+struct Stager {
+    static constexpr int kThreads = 4, kBufs = 2;
+    static constexpr size_t kChunkBytes = 4u << 20;
+    static constexpr size_t kMinBytes = 8u << 20;      // smaller transfers take the plain path
+    char* pinned[kThreads][kBufs] = {};
+    cudaStream_t st[kThreads] = {};
+    cudaEvent_t ev[kThreads][kBufs] = {};
+    cudaEvent_t ev_main = nullptr, ev_done[kThreads] = {};
+    bool ready = false;
+};
+
 struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
     long long kernels = 0;
@@ -156,6 +170,11 @@ struct Ctx {
 
     // data movement
     enum Which { W_U = 0, W_F = 1, W_R = 2 };
+    Stager stager;
+    void stager_init();
+    // rows [ya, yb) of a padded device array <-> the same rows of an n x n host vector in ordinary (pageable) memory
+    void copy_rows_staged(char* dev_row0, size_t dev_pitch_bytes, char* host_row0, size_t row_bytes, int rows, bool to_device);
+    void copy_rows(char* dev_row0, size_t dev_pitch_bytes, char* host_row0, size_t row_bytes, int rows, bool to_device);
     void set_host(int level, Which w, const void* host);
     void get_host(int level, Which w, void* host);
     void zero_u(int level);

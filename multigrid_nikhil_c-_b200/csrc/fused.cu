@@ -290,6 +290,8 @@ static bool stream_ok(const Ctx& ctx, const Level&)
     return (ctx.cfg.flags & MG_FUSED) != 0;
 }
 
+template <typename T> static void stream_sweeps(Ctx& ctx, Level& lv, int nu);
+
 // temporally blocked sweeps: returns the number of sweeps performed (0 = not applicable)
 template <typename T>
 int fused_jacobi(Ctx& ctx, Level& lv, int remaining, T, T)
@@ -300,6 +302,16 @@ int fused_jacobi(Ctx& ctx, Level& lv, int remaining, T, T)
     launch_stream<T, 2, MODE_SWEEPS, false>(ctx, lv, nullptr);
     return 2;
 }
+// red-black Gauss-Seidel sweeps through the streaming kernel: both colours of a sweep (and two sweeps when nu >= 2) in
+// one pass over the level, 3S bytes per point per launch instead of 6S per sweep with one k_rbgs launch per colour
+bool fused_rbgs(Ctx& ctx, Level& lv, int nu)
+{
+    if (!stream_ok(ctx, lv) || ctx.cfg.smoother != MG_SMOOTH_RBGS || nu < 1) return false;
+    if (ctx.f64()) stream_sweeps<double>(ctx, lv, nu);
+    else stream_sweeps<float>(ctx, lv, nu);
+    return true;
+}
+
 template int fused_jacobi<double>(Ctx&, Level&, int, double, double);
 template int fused_jacobi<float>(Ctx&, Level&, int, float, float);
 

@@ -9,6 +9,8 @@ namespace mgb {
 void fused_setup(Ctx& ctx);
 // run up to `remaining` temporally blocked Jacobi sweeps on level lv; returns the number done (0 = not applicable)
 template <typename T> int fused_jacobi(Ctx& ctx, Level& lv, int remaining, T c0, T c1);
+// `nu` red-black Gauss-Seidel sweeps through the streaming kernel (both colours per pass); false = not applicable
+bool fused_rbgs(Ctx& ctx, Level& lv, int nu);
 // run one whole cycle visit of `level` with fused kernels; false = caller runs the unfused sequence
 bool fused_cycle_level(Ctx& ctx, int level, int nu1, int nu2, int gamma);
 // `visits` (>= 2) consecutive visits of `level` with POST of visit v and PRE of visit v+1 fused into one POSTPRE launch

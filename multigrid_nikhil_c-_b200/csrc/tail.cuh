@@ -54,12 +54,12 @@ struct TailLv {
     __device__ __forceinline__ T* F() const { return buf + 2 * SZ; }
 };
 
-// Levels <= kTailWarpLevel are run by WARP 0 ALONE with __syncwarp() between the phases: a phase on a 15^2 (or smaller)
+// Levels <= kTailWarpLevel are run by WARP 0 ALONE with __syncwarp() between the phases: a phase on a 7^2 (or smaller)
 // grid is a few instructions per lane, and a 1024-thread block barrier costs more than the phase itself (ncu, round 2:
-// barrier + instruction-fetch stalls dominate k_tail; a W-cycle visits these levels 44 times per tail launch).  The other
+// barrier + instruction-fetch stalls dominate k_tail; a W-cycle visits these levels 40 times per tail launch).  The other
 // 31 warps wait at one block barrier for the whole sub-cycle.  Same arrays, same formulas, same bits.
 #ifndef MGB_TAIL_WARP_LEVEL
-#define MGB_TAIL_WARP_LEVEL 4
+#define MGB_TAIL_WARP_LEVEL 3   // measured on the B200 (profiles/r02_tail_variants.txt): 3 beats 0 (off) and 4
 #endif
 constexpr int kTailWarpLevel = MGB_TAIL_WARP_LEVEL;
 
