@@ -94,8 +94,9 @@ void Ctx::init()
     int halo_rows[32];
     for (int l = 0; l < 32; ++l) halo_rows[l] = kHaloRows;
     if (cfg.world > 1) {
+        // default (measured at 2 and 8 GPUs, profiles/r02_scaling.md); MGB200_COMM_AVOID=0 selects the lazy exchanges
         const char* e = getenv("MGB200_COMM_AVOID");
-        comm_avoid = e && e[0] == '1';
+        comm_avoid = !(e && e[0] == '0');
         if (comm_avoid) {
             const int ns = (cfg.smoother == MG_SMOOTH_RBGS) ? 4 : 2;
             int x[32], ex[32], need[32];
@@ -181,15 +182,9 @@ void Ctx::init()
     }
     if (cfg.world > 1) {
         comm = comm_create(*this);
+        // distributed cycles are captured (NCCL calls included) and replayed as CUDA graphs unless MGB200_GRAPH_DIST=0
         const char* e = getenv("MGB200_GRAPH_DIST");
-        graph_dist = e && e[0] == '1';
-        const char* ov = getenv("MGB200_OVERLAP");
-        overlap = ov && ov[0] == '1';
-        if (overlap) {
-            MG_CK(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
-            MG_CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-            MG_CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-        }
+        graph_dist = !(e && e[0] == '0');
     }
     {
         // both on by default (measured on the B200: profiles/r02a_*); "=0" switches one off for A/B timing
@@ -210,11 +205,7 @@ void Ctx::release() noexcept
     if (stream) cudaStreamSynchronize(stream);
     for (auto& kv : graphs)
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-    if (comm_stream) cudaStreamSynchronize(comm_stream);
-    if (ev_fork) cudaEventDestroy(ev_fork);
-    if (ev_join) cudaEventDestroy(ev_join);
     if (comm) comm_destroy(comm);
-    if (comm_stream) cudaStreamDestroy(comm_stream);
     for (auto& lv : levels)
         for (int k = 0; k < 4; ++k)
             if (lv.alloc[k]) cudaFree(lv.alloc[k]);
@@ -240,8 +231,6 @@ void Ctx::release() noexcept
     graphs.clear();
     levels.clear();
     comm = nullptr;
-    comm_stream = nullptr;
-    ev_fork = ev_join = nullptr;
     d_partials = d_norm = h_norm = nullptr;
     stream = nullptr;
 }

@@ -149,14 +149,11 @@ struct Ctx {
     FusedKnobs knobs;
     Comm* comm = nullptr;
     int aggl_level = 0;  // levels <= aggl_level are replicated on every rank
-    bool graph_dist = false;  // capture NCCL exchanges into cycle graphs (MGB200_GRAPH_DIST=1)
+    bool graph_dist = true;   // capture NCCL exchanges into cycle graphs (MGB200_GRAPH_DIST=0 turns it off)
     bool zero_guess = true;   // skip reading / writing the zero coarse guess (P:613) where the next kernel does not need it (MGB200_ZERO_GUESS=0 turns it off)
-    bool comm_avoid = false;  // communication-avoiding slab schedule (MGB200_COMM_AVOID=1, csrc/sched.h)
-    bool overlap = false;     // halo exchange on a second stream, overlapped with the interior rows (MGB200_OVERLAP=1)
+    bool comm_avoid = true;   // communication-avoiding slab schedule (csrc/sched.h; MGB200_COMM_AVOID=0 turns it off)
     // tolerance loop: the cycle's last kernel on the finest level also leaves sum r^2 in d_norm (fused.cu: launch_post_norm)
     bool want_post_norm = false, post_norm_done = false;
-    cudaStream_t comm_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool chain = true;        // fuse POST of one visit of a level with PRE of the next (stream.cuh MODE_POSTPRE; MGB200_CHAIN=0 turns it off)
 
     explicit Ctx(const mg_config& c);

@@ -237,38 +237,13 @@ static void launch_stream(Ctx& ctx, Level& lv, Level* lcv)
     constexpr int du = C::HT - (MODE == MODE_POST ? 1 : 0);
     constexpr int df = NS + (MODE == MODE_PRE ? 1 : 0) - (MODE == MODE_SWEEPS ? 1 : 0);
     constexpr int dc = (MODE == MODE_POST) ? NS / 2 + 1 : 0;
-    // rows whose pipeline reaches into a halo row (of u, f or, for POST, of the coarse correction), generously
-    constexpr int kEdge = ((C::HT > C::HB ? C::HT : C::HB) + 4 + 1) & ~1;
-    const bool need_u = lv.distributed && lv.hv_u < du;
-    const bool need_f = lv.distributed && df > 0 && lv.hv_f < df;
-    const bool need_c = MODE == MODE_POST && lcv->distributed && lcv->hv_u < dc;
-    if (ctx.overlap && ctx.comm_stream && lv.distributed && (need_u || need_f || need_c) &&
-        lv.own_hi - lv.own_lo >= 4 * kEdge) {
-        // MGB200_OVERLAP: the exchange runs on a second stream while the interior rows -- whose pipeline touches no
-        // halo row -- are computed; the two edge blocks follow once the halos have arrived (fork / join by events,
-        // capturable).  Same rows, same arithmetic, only the launch is split in three.
-        MG_REQUIRE(du <= lv.halo && df <= lv.halo && (!need_c || dc <= lcv->halo), "halo depth exceeds the stored halo");
-        if (MODE == MODE_PRE) lcv->cur = 0;
-        MG_CK(cudaEventRecord(ctx.ev_fork, ctx.stream));
-        MG_CK(cudaStreamWaitEvent(ctx.comm_stream, ctx.ev_fork, 0));
-        if (need_u) { comm_halo_exchange(ctx, lv, lv.u[lv.cur], du, ctx.comm_stream); lv.hv_u = du; }
-        if (need_f) { comm_halo_exchange(ctx, lv, lv.f, df, ctx.comm_stream); lv.hv_f = df; }
-        if (need_c) { comm_halo_exchange(ctx, *lcv, lcv->u[lcv->cur], dc, ctx.comm_stream); lcv->hv_u = dc; }
-        MG_CK(cudaEventRecord(ctx.ev_join, ctx.comm_stream));
-        const int ry = tuned_ry<T, NS, MODE, RBGS>(ctx, lv, lcv);
-        raw_launch<T, NS, MODE, RBGS>(ctx, make_args<T, NS, MODE>(ctx, lv, lcv, ry, lv.own_lo + kEdge, lv.own_hi - kEdge));
-        MG_CK(cudaStreamWaitEvent(ctx.stream, ctx.ev_join, 0));
-        raw_launch<T, NS, MODE, RBGS>(ctx, make_args<T, NS, MODE>(ctx, lv, lcv, ry, lv.own_lo, lv.own_lo + kEdge));
-        raw_launch<T, NS, MODE, RBGS>(ctx, make_args<T, NS, MODE>(ctx, lv, lcv, ry, lv.own_hi - kEdge, lv.own_hi));
-    } else {
-        ctx.ensure_halo(lv, Ctx::W_U, du);
-        ctx.ensure_halo(lv, Ctx::W_F, df);
-        if (MODE == MODE_PRE) lcv->cur = 0;
-        if (MODE == MODE_POST) ctx.ensure_halo(*lcv, Ctx::W_U, dc);
-        const int ry = tuned_ry<T, NS, MODE, RBGS>(ctx, lv, lcv);
-        const StreamArgs<T> a = make_args<T, NS, MODE>(ctx, lv, lcv, ry);
-        raw_launch<T, NS, MODE, RBGS>(ctx, a);
-    }
+    ctx.ensure_halo(lv, Ctx::W_U, du);
+    ctx.ensure_halo(lv, Ctx::W_F, df);
+    if (MODE == MODE_PRE) lcv->cur = 0;
+    if (MODE == MODE_POST) ctx.ensure_halo(*lcv, Ctx::W_U, dc);
+    const int ry = tuned_ry<T, NS, MODE, RBGS>(ctx, lv, lcv);
+    const StreamArgs<T> a = make_args<T, NS, MODE>(ctx, lv, lcv, ry);
+    raw_launch<T, NS, MODE, RBGS>(ctx, a);
     lv.cur ^= 1;
     lv.hv_u = 0;
     if (MODE == MODE_PRE) {
@@ -457,7 +432,7 @@ template <typename T>
 static void post_fused(Ctx& ctx, Level& lv, Level& lcv, int nu2)
 {
     const int k = std::min(nu2, 2);
-    if (ctx.want_post_norm && lv.level == ctx.cfg.finest_level && nu2 == k && !ctx.overlap) {
+    if (ctx.want_post_norm && lv.level == ctx.cfg.finest_level && nu2 == k) {
         bool done;
         if (ctx.cfg.smoother == MG_SMOOTH_JACOBI) done = (k == 2) ? launch_post_norm<T, 2, false>(ctx, lv, &lcv) : launch_post_norm<T, 1, false>(ctx, lv, &lcv);
         else done = (k == 2) ? launch_post_norm<T, 4, true>(ctx, lv, &lcv) : launch_post_norm<T, 2, true>(ctx, lv, &lcv);

@@ -21,7 +21,7 @@ import mgb200  # noqa: E402
 import oracle  # noqa: E402
 
 mgdist = __import__("importlib").import_module("multigrid_nikhil_c-_b200.dist")
-KNOBS = ("MGB200_COMM_AVOID", "MGB200_GRAPH_DIST", "MGB200_OVERLAP", "MGB200_CHAIN", "MGB200_ZERO_GUESS")
+KNOBS = ("MGB200_COMM_AVOID", "MGB200_GRAPH_DIST", "MGB200_CHAIN", "MGB200_ZERO_GUESS")
 
 
 def main():

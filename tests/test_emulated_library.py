@@ -48,9 +48,9 @@ def torchrun_cmd(world, script, *args):
 
 WORKER = os.path.join(ROOT, "tests", "mgpu_worker.py")
 BENCH_WORKER = os.path.join(ROOT, "tests", "host_emul", "bench_emu_worker.py")
-KNOBS = {"default": {}, "comm_avoid+graph_dist": {"MGB200_COMM_AVOID": "1", "MGB200_GRAPH_DIST": "1"},
-         "no_chain_no_zero_guess": {"MGB200_CHAIN": "0", "MGB200_ZERO_GUESS": "0"}, "graph_dist": {"MGB200_GRAPH_DIST": "1"},
-         "overlap+graph_dist": {"MGB200_OVERLAP": "1", "MGB200_GRAPH_DIST": "1"}}
+KNOBS = {"default": {}, "lazy_exchanges_eager": {"MGB200_COMM_AVOID": "0", "MGB200_GRAPH_DIST": "0"},
+         "no_chain_no_zero_guess": {"MGB200_CHAIN": "0", "MGB200_ZERO_GUESS": "0"}, "lazy_exchanges_graph": {"MGB200_COMM_AVOID": "0"},
+         "comm_avoid_eager": {"MGB200_GRAPH_DIST": "0"}}
 BENCH = {"1rank": (1, []), "2ranks_slab_host_buffers": (2, ["--aggl", "5", "--level", "8"]), "rbgs_wcycle": (1, ["--smoother", "rbgs", "--gamma", "2"])}
 
 
@@ -129,11 +129,11 @@ def test_two_rank_row_slabs_under_emulation(jobs, name):
     """tests/mgpu_worker.py on 2 CPU ranks: gloo bootstrap, emulated NCCL; every rank's rows equal the oracle's."""
     out = jobs.result("slabs:" + name)
     assert "MGPU OK world=2" in out, out[-3000:]
-    if KNOBS[name].get("MGB200_COMM_AVOID") == "1":
-        # the communication-avoiding plan really ran: far fewer point-to-point messages than the default schedule
+    if KNOBS[name].get("MGB200_COMM_AVOID") == "0":
+        # the communication-avoiding plan (the default) really runs: far fewer point-to-point messages than the lazy exchanges
         sends = int(out.split("sends=")[1].split()[0])
         default_sends = int(jobs.result("slabs:default").split("sends=")[1].split()[0])
-        assert sends < 0.75 * default_sends, (sends, default_sends)
+        assert default_sends < 0.75 * sends, (sends, default_sends)
 
 
 BENCH_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",

@@ -10,8 +10,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("env", [{"MGB200_COMM_AVOID": "1"}, {"MGB200_GRAPH_DIST": "1"},
-                                 {"MGB200_COMM_AVOID": "1", "MGB200_GRAPH_DIST": "1"}])
+@pytest.mark.parametrize("env", [{"MGB200_COMM_AVOID": "0"}, {"MGB200_GRAPH_DIST": "0"},
+                                 {"MGB200_COMM_AVOID": "0", "MGB200_GRAPH_DIST": "0"}, {"MGB200_CHAIN": "0", "MGB200_ZERO_GUESS": "0"}])
 def test_multigpu_optin_paths(env):
     import torch
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
