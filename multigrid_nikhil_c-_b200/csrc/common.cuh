@@ -17,6 +17,19 @@
 namespace mgb {
 
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still running; pdl_wait() blocks until the predecessor grid has completed
+// and its memory is visible, pdl_trigger() lets the NEXT kernel of the stream start its own launch early.  Every kernel
+// of a cycle calls both first thing, so the ~2-3 us launch latency of each kernel hides behind the one before it while
+// the data dependencies stay exactly those of ordinary stream order.  No-ops for kernels launched without the attribute.
+#if defined(MGB_EMU) || !defined(__CUDA_ARCH__)
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_trigger() {}
+#else
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 template <typename T> struct Vec;
 template <> struct Vec<double> { static constexpr int N = 2; typedef double2 type; };
 template <> struct Vec<float>  { static constexpr int N = 4; typedef float4 type; };

@@ -82,6 +82,7 @@ void fused_setup(Ctx& ctx)
     k.force_ry_minN = env_int("MGB200_STREAM_RY_MINN", 4096);
     k.occ = std::max(1, env_int("MGB200_STREAM_OCC", 12));
     k.autotune = env_int("MGB200_AUTOTUNE", 1) != 0;
+    k.pdl = env_int("MGB200_PDL", 0) != 0;
     if (ctx.f64()) { set_attrs_t<double>(); set_attrs_chain<double>(); }
     else { set_attrs_t<float>(); set_attrs_chain<float>(); }
 }
@@ -166,6 +167,27 @@ static size_t stream_smem(const Ctx& ctx)
     return std::min<size_t>(100 * 1024, std::max<size_t>(C::SMEM_BYTES, (size_t)(227 * 1024) / std::max(1, ctx.knobs.occ / kStreamWarps) - 1024));
 }
 
+// One kernel launch on the context's stream; with knobs.pdl as a programmatic dependent launch (common.cuh: pdl_wait),
+// which also holds inside stream capture (the graph gets a programmatic edge).
+template <typename... KP, typename... A>
+static void launch_k(Ctx& ctx, void (*kernel)(KP...), unsigned grid, unsigned block, size_t smem, A&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx.stream;
+    cudaLaunchAttribute at[1];
+    if (ctx.knobs.pdl) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+    }
+    MG_CK(cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...));
+    ++ctx.lc.n;
+}
+
 template <typename T, int NS, int MODE, bool RBGS>
 static void raw_launch(Ctx& ctx, const StreamArgs<T>& a)
 {
@@ -173,13 +195,8 @@ static void raw_launch(Ctx& ctx, const StreamArgs<T>& a)
     if (a.yb <= a.ya) return;
     const unsigned grid = cdiv(a.nitems, kStreamWarps);
     const size_t smem = stream_smem<C>(ctx);
-    if constexpr (MODE == MODE_POSTPRE) {
-        k_stream_chain<T, NS, RBGS><<<grid, kStreamWarps * 32, smem, ctx.stream>>>(a);
-    } else {
-        k_stream<T, NS, MODE, RBGS><<<grid, kStreamWarps * 32, smem, ctx.stream>>>(a);
-    }
-    ++ctx.lc.n;
-    MG_CK(cudaGetLastError());
+    if constexpr (MODE == MODE_POSTPRE) launch_k(ctx, k_stream_chain<T, NS, RBGS>, grid, kStreamWarps * 32, smem, a);
+    else launch_k(ctx, k_stream<T, NS, MODE, RBGS>, grid, kStreamWarps * 32, smem, a);
 }
 
 // Chunk height per (level, kernel): on the big levels the best height depends on how strips x chunks maps
@@ -319,9 +336,7 @@ static void launch_pre_zero_guess(Ctx& ctx, Level& lv, Level* lcv, bool write_ze
     if (a.yb > a.ya) {
         typedef StreamCfg<T, NS, MODE_PRE> C;
         const size_t smem = stream_smem<C>(ctx);
-        k_stream_pre_zg<T, NS, RBGS><<<cdiv(a.nitems, kStreamWarps), kStreamWarps * 32, smem, ctx.stream>>>(a);
-        ++ctx.lc.n;
-        MG_CK(cudaGetLastError());
+        launch_k(ctx, k_stream_pre_zg<T, NS, RBGS>, cdiv(a.nitems, kStreamWarps), kStreamWarps * 32, smem, a);
     }
     lv.cur ^= 1;
     lv.hv_u = 0;
@@ -418,11 +433,8 @@ static bool launch_post_norm(Ctx& ctx, Level& lv, Level* lcv)
     ctx.ensure_halo(lv, Ctx::W_U, C::HT - 1);
     ctx.ensure_halo(lv, Ctx::W_F, NS);
     ctx.ensure_halo(*lcv, Ctx::W_U, (NS + 2) / 2 + 1);
-    k_stream_norm<T, NS, MODE_POST, RBGS><<<cdiv(a.nitems, kStreamWarps), kStreamWarps * 32, stream_smem<C>(ctx), ctx.stream>>>(a, ctx.d_partials);
-    ++ctx.lc.n;
-    MG_CK(cudaGetLastError());
-    launch_sum_partials(ctx.stream, ctx.lc, ctx.d_partials, a.nitems, ctx.d_norm);
-    MG_CK(cudaGetLastError());
+    launch_k(ctx, k_stream_norm<T, NS, MODE_POST, RBGS>, cdiv(a.nitems, kStreamWarps), kStreamWarps * 32, stream_smem<C>(ctx), a, ctx.d_partials);
+    launch_k(ctx, k_sum_partials, 1u, 256u, (size_t)0, (const double*)ctx.d_partials, a.nitems, ctx.d_norm);
     lv.cur ^= 1;
     lv.hv_u = 0;
     return true;
@@ -518,9 +530,7 @@ static void launch_fmg_entry(Ctx& ctx, Level& lv, Level& lcv, bool write_zero_gu
     StreamArgs<T> a = make_args<T, NS, MODE_POSTPRE>(ctx, lv, &lcv, 0, -1, -1, write_zero_guess);
     if (a.yb > a.ya) {
         const size_t smem = stream_smem<C>(ctx);
-        k_stream_fmg_entry<T, NS, RBGS><<<cdiv(a.nitems, kStreamWarps), kStreamWarps * 32, smem, ctx.stream>>>(a);
-        ++ctx.lc.n;
-        MG_CK(cudaGetLastError());
+        launch_k(ctx, k_stream_fmg_entry<T, NS, RBGS>, cdiv(a.nitems, kStreamWarps), kStreamWarps * 32, smem, a);
     }
     lv.cur ^= 1;
     lv.hv_u = 0;
@@ -580,14 +590,12 @@ static void run_tail(Ctx& ctx, int level, int nu1, int nu2, int gamma)
     a.pitch = lv.pitch;
     const size_t smem = tail_smem_bytes<T>(level, a.coarsest);
     if (lv.u_zero) {   // zero-guess chain: u is logically zero and is not read
-        if (ctx.cfg.smoother == MG_SMOOTH_RBGS) k_tail_zg<T, true><<<1, kTailThreads, smem, ctx.stream>>>(a);
-        else k_tail_zg<T, false><<<1, kTailThreads, smem, ctx.stream>>>(a);
+        if (ctx.cfg.smoother == MG_SMOOTH_RBGS) launch_k(ctx, k_tail_zg<T, true>, 1u, (unsigned)kTailThreads, smem, a);
+        else launch_k(ctx, k_tail_zg<T, false>, 1u, (unsigned)kTailThreads, smem, a);
         lv.u_zero = false;
         lv.hv_u = lv.halo;
-    } else if (ctx.cfg.smoother == MG_SMOOTH_RBGS) k_tail<T, true><<<1, kTailThreads, smem, ctx.stream>>>(a);
-    else k_tail<T, false><<<1, kTailThreads, smem, ctx.stream>>>(a);
-    ++ctx.lc.n;
-    MG_CK(cudaGetLastError());
+    } else if (ctx.cfg.smoother == MG_SMOOTH_RBGS) launch_k(ctx, k_tail<T, true>, 1u, (unsigned)kTailThreads, smem, a);
+    else launch_k(ctx, k_tail<T, false>, 1u, (unsigned)kTailThreads, smem, a);
 }
 
 // ---------------------------------------------------------------------------------

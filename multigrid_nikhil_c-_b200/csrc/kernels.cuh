@@ -174,6 +174,8 @@ k_residual(const T* __restrict__ u, const T* __restrict__ f, T* __restrict__ r,
 static __global__ void __launch_bounds__(256)
 k_sum_partials(const double* __restrict__ partials, int count, double* __restrict__ out)
 {
+    pdl_wait();
+    pdl_trigger();
     double acc = 0.0;
     for (int i = threadIdx.x; i < count; i += 256) acc += partials[i];
 #pragma unroll

@@ -503,6 +503,8 @@ template <typename T, int NS, int MODE, bool RBGS>
 __global__ void __launch_bounds__(kStreamWarps * 32, kStreamMinCtas / kStreamWarps)
 k_stream(const StreamArgs<T> a)
 {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(16) unsigned char stream_smem[];
     const int warp = threadIdx.x >> 5;
     const int item = blockIdx.x * kStreamWarps + warp;
@@ -516,6 +518,8 @@ template <typename T, int NS, int MODE, bool RBGS>
 __global__ void __launch_bounds__(kStreamWarps * 32, kStreamMinCtas / kStreamWarps)
 k_stream_norm(const StreamArgs<T> a, double* __restrict__ partials)
 {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(16) unsigned char stream_smem[];
     const int warp = threadIdx.x >> 5;
     const int item = blockIdx.x * kStreamWarps + warp;
@@ -534,6 +538,8 @@ template <typename T, int NS, bool RBGS>
 __global__ void __launch_bounds__(kStreamWarps * 32, kStreamChainMinCtas / kStreamWarps)
 k_stream_chain(const StreamArgs<T> a)
 {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(16) unsigned char stream_smem[];
     const int warp = threadIdx.x >> 5;
     const int item = blockIdx.x * kStreamWarps + warp;
@@ -547,6 +553,8 @@ template <typename T, int NS, bool RBGS>
 __global__ void __launch_bounds__(kStreamWarps * 32, kStreamChainMinCtas / kStreamWarps)
 k_stream_fmg_entry(const StreamArgs<T> a)
 {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(16) unsigned char stream_smem[];
     const int warp = threadIdx.x >> 5;
     const int item = blockIdx.x * kStreamWarps + warp;
@@ -560,6 +568,8 @@ template <typename T, int NS, bool RBGS>
 __global__ void __launch_bounds__(kStreamWarps * 32, kStreamMinCtas / kStreamWarps)
 k_stream_pre_zg(const StreamArgs<T> a)
 {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(16) unsigned char stream_smem[];
     const int warp = threadIdx.x >> 5;
     const int item = blockIdx.x * kStreamWarps + warp;

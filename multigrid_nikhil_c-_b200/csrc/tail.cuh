@@ -234,6 +234,8 @@ template <typename T, bool RBGS>
 __global__ void __launch_bounds__(kTailThreads, 1)   // one CTA per SM: 64 registers per thread (the default heuristic caps at 32 and spills)
 k_tail(const TailArgs<T> a)
 {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(16) unsigned char tail_smem[];
     T* base = reinterpret_cast<T*>(tail_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -256,6 +258,8 @@ template <typename T, bool RBGS>
 __global__ void __launch_bounds__(kTailThreads, 1)   // one CTA per SM: 64 registers per thread (the default heuristic caps at 32 and spills)
 k_tail_zg(const TailArgs<T> a)
 {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(16) unsigned char tail_smem[];
     T* base = reinterpret_cast<T*>(tail_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -67,7 +67,7 @@ enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFu
 enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal = 0, cudaStreamCaptureModeThreadLocal = 1, cudaStreamCaptureModeRelaxed = 2 };
 enum { cudaStreamNonBlocking = 1 };
 enum { cudaEventDefault = 0, cudaEventBlockingSync = 1, cudaEventDisableTiming = 2 };
-enum cudaLaunchAttributeID { cudaLaunchAttributeClusterDimension = 4 };
+enum cudaLaunchAttributeID { cudaLaunchAttributeClusterDimension = 4, cudaLaunchAttributeProgrammaticStreamSerialization = 6 };
 
 struct emuStream;
 struct emuEvent;
@@ -84,7 +84,7 @@ struct cudaDeviceProp {
     size_t totalGlobalMem;
     int major, minor;
 };
-struct cudaLaunchAttributeValue { struct { unsigned x, y, z; } clusterDim; };
+struct cudaLaunchAttributeValue { struct { unsigned x, y, z; } clusterDim; int programmaticStreamSerializationAllowed; };
 struct cudaLaunchAttribute { cudaLaunchAttributeID id; cudaLaunchAttributeValue val; };
 struct cudaLaunchConfig_t {
     dim3 gridDim, blockDim;
