@@ -144,13 +144,18 @@ void Ctx::init()
         lv.r = (char*)lv.alloc[3] - off;
     }
     {
-        // one partial per residual block; a replicated level below a distributed finest level stores more rows than the
-        // finest slab does, so the capacity is the maximum over all levels
+        // One partial per residual block (k_residual) or per streaming work item (k_stream_norm: at most one item per 8 rows
+        // and per strip of >= 48 columns).  The capacity is the maximum over all levels and must NOT depend on the rank: a
+        // rank-dependent capacity once made edge ranks fall back to another kernel -- with other halo depths -- than their
+        // neighbours.  Distributed levels therefore count N / world + 2 * halo rows whatever this rank stores.
         const int V = f64() ? 2 : 4;
         partials_cap = 0;
         for (int l = cfg.coarsest_level; l <= cfg.finest_level; ++l) {
             const Level& lv = levels[l];
-            partials_cap = std::max(partials_cap, (int)(cdiv(lv.N, V * kTX) * cdiv(lv.st_hi - lv.st_lo, 2)) + 8);
+            const i64 rows = lv.distributed ? (i64)lv.N / cfg.world + 2 * lv.halo + 2 : (i64)lv.N + 1;
+            const i64 resid = (i64)cdiv(lv.N, V * kTX) * cdiv(rows, 2);
+            const i64 items = (i64)cdiv(lv.N, 48) * (cdiv(rows, 8) + 1);
+            partials_cap = std::max(partials_cap, (int)std::max(resid, items) + 8);
         }
         MG_CK(cudaMalloc(&d_partials, sizeof(double) * (size_t)partials_cap));
         MG_CK(cudaMalloc(&d_norm, sizeof(double) * 8));

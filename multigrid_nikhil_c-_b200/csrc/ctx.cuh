@@ -104,7 +104,7 @@ struct FusedKnobs {
     bool autotune = true;      // MGB200_AUTOTUNE=0 disables the chunk-height tuner
     int force_ry = 0;          // MGB200_STREAM_RY / _MINN: force the chunk height on levels with N >= minN (tuning sweeps)
     int force_ry_minN = 4096;
-    bool pdl = false;          // programmatic dependent launches between the kernels of a cycle (MGB200_PDL)
+    bool pdl = true;           // programmatic dependent launches between the kernels of a cycle (MGB200_PDL=0 turns them off)
 };
 
 // Staging of PAGEABLE host vectors (the std::vector call shape of include/mgb200_driver.hpp): a cudaMemcpy from pageable

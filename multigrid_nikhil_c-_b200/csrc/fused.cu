@@ -82,7 +82,7 @@ void fused_setup(Ctx& ctx)
     k.force_ry_minN = env_int("MGB200_STREAM_RY_MINN", 4096);
     k.occ = std::max(1, env_int("MGB200_STREAM_OCC", 12));
     k.autotune = env_int("MGB200_AUTOTUNE", 1) != 0;
-    k.pdl = env_int("MGB200_PDL", 0) != 0;
+    k.pdl = env_int("MGB200_PDL", 1) != 0;   // measured: -2.6 % on the 4097^2 cycle, -1.5 % on the 8193^2 W-cycle (profiles/r02_kernel_experiments.md)
     if (ctx.f64()) { set_attrs_t<double>(); set_attrs_chain<double>(); }
     else { set_attrs_t<float>(); set_attrs_chain<float>(); }
 }
@@ -429,7 +429,8 @@ static bool launch_post_norm(Ctx& ctx, Level& lv, Level* lcv)
     ctx.materialize_u(lv);
     ctx.materialize_u(*lcv);
     StreamArgs<T> a = make_args<T, NS, MODE_POST, true>(ctx, lv, lcv, ry);
-    if (a.nitems > ctx.partials_cap || a.yb <= a.ya) return false;
+    MG_REQUIRE(a.nitems <= ctx.partials_cap, "partials buffer too small for the norm kernel");   // (never rank-dependent)
+    if (a.yb <= a.ya) return false;
     ctx.ensure_halo(lv, Ctx::W_U, C::HT - 1);
     ctx.ensure_halo(lv, Ctx::W_F, NS);
     ctx.ensure_halo(*lcv, Ctx::W_U, (NS + 2) / 2 + 1);

@@ -25,14 +25,6 @@
 // expression, in the same order, as in the unfused kernels (common.cuh), so results are
 // bit-identical to them and to the oracle.
 //
-// SKEWED PIPELINE (round 2).  Within one step every stage reads only what EARLIER steps produced: the stages run in
-// reverse order (restriction, residual, stage NS ... stage 1, stage 0), stage s works on row y-2s instead of y-s, and the
-// register window of u_(s-1) it reads was completed in the previous step.  Nothing a stage computes is consumed in the
-// same step, so the NS+2 stages of a step are independent instruction streams -- the dependent chain per row is one
-// stage long instead of NS+2 (shuffle + fp64 chain each), which is what bounded the deep kernels (red-black NS = 4,
-// POST+PRE chains) at ~0.55 of the HBM roofline with 12 resident warps per SM.  Cost: f of a row is read from the ring up
-// to 2NS+2 steps after it arrived, so u and f live in separate rings (u is dead after stage 0: 6 slots; f: 12 or 24).
-//
 // The kernel is instruction-issue sensitive (profiles/r01_v2_*: 69 % issue utilisation,
 // half of it integer work), hence:
 //  - the ring has 12 slots = 4 blocks of 3; the row loop is unrolled by 3 so that window
@@ -56,14 +48,12 @@ constexpr bool mode_has_pre(int m) { return m == MODE_PRE || m == MODE_POSTPRE; 
 
 constexpr int kStreamWarps = 1;  // warps (independent work items) per CTA.  4 lock-stepped warps per CTA (bar.sync every 3 rows)
                                  // were measured slower and more erratic (profiles/r01_tune_stream.txt)
-// Rings (per warp, slots of one row each, organised in blocks of 3 slots = one trip of the 3x unrolled row loop; the
-// number of blocks is a power of two so that block indices wrap with a mask):
-//   u ring  kUBlocks = 2 (6 slots): a row is prefetched kPrefetch = 5 steps ahead and read once, by stage 0, as it arrives
-//   f ring  4 or 8 blocks: stage s reads f of row y-2s, the residual of row y-2NS-2
-//   c ring  4 blocks (POST): stage 0 interpolates from the coarse rows of steps y and y-1
-constexpr int kPrefetch = 5;
-constexpr int kUBlocks = 2;
-constexpr int kCBlocks = 4;
+// ring slots per warp: NB blocks of 3 slots, NB a power of two.  12 slots prefetch D = 9 - NS rows ahead; the deep ring
+// (24 slots, D = 21 - NS) keeps more bytes in flight per warp at the price of fewer resident warps (shared memory).
+#ifndef MGB_DEEP_RING_MIN_NS
+#define MGB_DEEP_RING_MIN_NS 99   // kernels with NS >= this use the deep ring (build-time experiment switch)
+#endif
+constexpr int ring_slots(int ns) { return ns >= MGB_DEEP_RING_MIN_NS ? 24 : 12; }
 
 // NORM (POST only): one more pipeline stage computes the residual of the OUTPUT iterate and accumulates its sum of
 // squares (the convergence check of the tolerance loop, P:604-608 shape) -- no separate residual pass over the grid.
@@ -73,7 +63,6 @@ struct StreamCfg {
     static constexpr bool HAS_POST = mode_has_post(MODE), HAS_PRE = mode_has_pre(MODE);
     static constexpr bool HAS_RES = HAS_PRE || NORM;                                    // residual stage after stage NS
     static_assert(!(NORM && HAS_PRE), "NORM is a POST / SWEEPS option");
-    // data dependencies (what the host needs for halo depths and strip overlap; independent of the pipeline skew)
     static constexpr int HL = NS + (HAS_PRE ? 2 : 0) + (NORM ? 1 : 0);                  // columns needed to the left
     static constexpr int HR = NS + (HAS_RES ? 1 : 0) + (HAS_POST ? 1 : 0);              // ... to the right
     static constexpr int HMAX = HL > HR ? HL : HR;
@@ -81,20 +70,16 @@ struct StreamCfg {
     static constexpr int OUTW = 32 * V - 2 * V * HLANES;                                // output columns per strip
     static constexpr int HT = NS + (HAS_PRE ? 2 : 0) + (NORM ? 1 : 0) + (HAS_POST ? 1 : 0);   // rows needed above
     static constexpr int HB = NS + (HAS_PRE ? 2 : 0) + (NORM ? 1 : 0);                  // rows needed below
-    // pipeline timing: at step y stage s produces row y - 2s, the residual row y - 2NS - 2, the restriction the coarse
-    // row centred on fine row y - 2NS - 4
-    static constexpr int DRAIN = 2 * NS + (HAS_PRE ? 4 : 0) + (NORM ? 2 : 0);           // steps after the last output row arrived
-    static constexpr int FBACK = 2 * NS + (HAS_RES ? 2 : 0);                            // oldest row of f still read
-    static constexpr int D = kPrefetch;
-    static constexpr int NBU = kUBlocks, NBC = kCBlocks;
-    static constexpr int NBF = (D + FBACK + 1 <= 12) ? 4 : 8;
-    static_assert(D + 1 <= 3 * NBU && D + FBACK + 1 <= 3 * NBF && D + 2 <= 3 * NBC, "ring too shallow");
+    static constexpr int DEPTH = ring_slots(NS);
+    static constexpr int NB = DEPTH / 3;                                                // ring blocks (power of two)
+    static constexpr int D = DEPTH - NS - 3;                                            // prefetch distance (rows)
     static constexpr int NW = NS + (HAS_RES ? 1 : 0);                                   // register windows of u_s
-    static constexpr int SLOT_ELEMS = 32 * V;                                           // one row of u (or f) per slot
+    // slot: [u: 32 V][f: 32 V]; POST keeps the coarse rows in a second, half-rate ring
+    static constexpr int SLOT_ELEMS = 32 * V * 2;
     static constexpr int CSLOT_ELEMS = 32 * (V / 2);
-    static constexpr int U_ELEMS = 3 * NBU * SLOT_ELEMS, F_ELEMS = 3 * NBF * SLOT_ELEMS, C_ELEMS = HAS_POST ? 3 * NBC * CSLOT_ELEMS : 0;
-    static constexpr int WARP_ELEMS = U_ELEMS + F_ELEMS + C_ELEMS;
+    static constexpr int WARP_ELEMS = DEPTH * SLOT_ELEMS + (HAS_POST ? DEPTH * CSLOT_ELEMS : 0);
     static constexpr size_t SMEM_BYTES = (size_t)kStreamWarps * WARP_ELEMS * sizeof(T);
+    static_assert(D >= 3, "ring too shallow");
 };
 
 template <typename T>
@@ -154,18 +139,15 @@ struct Streamer {
     static constexpr unsigned FULL = 0xffffffffu;
     static constexpr int BLK = 3 * C::SLOT_ELEMS;    // elements per ring block (3 slots)
     static constexpr int CBLK = 3 * C::CSLOT_ELEMS;
-    static constexpr int NBU = C::NBU, NBF = C::NBF, NBC = C::NBC;
 
     const StreamArgs<T>& a;
-    T* uring;      // this lane's 16 bytes of slot 0 of the u ring
-    T* fring;      // ... of the f ring
+    T* ring;       // this lane's 16 bytes of slot 0 (u part)
     T* cring;      // POST: this lane's 8 bytes of coarse slot 0
-    T* ublk[NBU];  // xblk[j] = ring block (q + j) & (NB - 1) for the current outer iteration q
-    T* fblk[NBF];
-    T* cblk[NBC];
+    static constexpr int NB = C::NB;
+    T* blk[NB];    // blk[j] = ring block (q + j) & (NB - 1) for the current outer iteration q
+    T* cblk[NB];
     int c;         // first column of this lane
     int y0, y1;
-    int y_need;    // last input row any stored output depends on (rows beyond it are not fetched)
     bool lane_ld, lane_ldc, lane_st;  // per-lane load / store flags
     typedef typename std::conditional<sizeof(T) == 8, unsigned long long, unsigned>::type MaskT;
     MaskT cm[V];   // all-ones for interior columns, 0 where the column must hold zero (Dirichlet ring / beyond the grid)
@@ -183,34 +165,40 @@ struct Streamer {
 
     __device__ __forceinline__ Streamer(const StreamArgs<T>& a_) : a(a_) {}
 
-    // ring slot of row (current step row - BACK), for phase PH of the unrolled loop: block pointer + constant
-    template <int NB, int PH, int BACK>
-    static __device__ __forceinline__ T* slot_of(T* const (&blocks)[NB], int slot_elems)
+    // ring slot of row (current step row - back), for phase PH: block pointer + constant
+    template <int PH, int BACK>
+    __device__ __forceinline__ T* rslot() const
     {
         constexpr int rel = PH - BACK;                       // slot index relative to this iteration's block
         constexpr int b = (rel >= 0) ? rel / 3 : -((-rel + 2) / 3);
         constexpr int s = rel - 3 * b;
-        return blocks[((b % NB) + NB) % NB] + s * slot_elems;
+        return blk[(b + NB) & (NB - 1)] + s * C::SLOT_ELEMS;
     }
-    template <int PH> __device__ __forceinline__ T* uslot() const { return slot_of<NBU, PH, 0>(ublk, C::SLOT_ELEMS); }
-    template <int PH, int BACK> __device__ __forceinline__ T* fslot() const { return slot_of<NBF, PH, BACK>(fblk, C::SLOT_ELEMS); }
-    template <int PH, int BACK> __device__ __forceinline__ T* cslot() const { return slot_of<NBC, PH, BACK>(cblk, C::CSLOT_ELEMS); }
+    template <int PH, int BACK>
+    __device__ __forceinline__ T* cslot() const
+    {
+        constexpr int rel = PH - BACK;
+        constexpr int b = (rel >= 0) ? rel / 3 : -((-rel + 2) / 3);
+        constexpr int s = rel - 3 * b;
+        return cblk[(b + NB) & (NB - 1)] + s * C::CSLOT_ELEMS;
+    }
 
-    // prefetch row y into the slots that are REL slots ahead of this iteration's block start
+    // prefetch row y into the slot that is REL slots ahead of this iteration's block start
     template <int REL>
     __device__ __forceinline__ void issue(int y)
     {
         constexpr int b = REL / 3, s = REL % 3;
-        const bool v = lane_ld && (y >= a.row_lo) && (y < a.row_hi) && (y <= y_need);
-        if (!ZG) cp_async16(ublk[b % NBU] + s * C::SLOT_ELEMS, v ? g_u : safe_u, v);
-        cp_async16(fblk[b % NBF] + s * C::SLOT_ELEMS, v ? g_f : safe_f, v);
+        T* dst = blk[b & (NB - 1)] + s * C::SLOT_ELEMS;
+        const bool v = lane_ld && (y >= a.row_lo) && (y < a.row_hi);
+        if (!ZG) cp_async16(dst, v ? g_u : safe_u, v);
+        cp_async16(dst + 32 * V, v ? g_f : safe_f, v);
         g_u += a.pitch;
         g_f += a.pitch;
         if (C::HAS_POST) {
             // coarse row ceil(y/2): a new one starts at every odd y; even rows re-read the previous one (L1 hit)
             const int ic = (y + 1) >> 1;
-            const bool vc = lane_ldc && (ic >= a.crow_lo) && (ic < a.crow_hi) && (y >= 0) && (y <= y_need);
-            cp_async8(cblk[b % NBC] + s * C::CSLOT_ELEMS, vc ? g_c : safe_c, vc);
+            const bool vc = lane_ldc && (ic >= a.crow_lo) && (ic < a.crow_hi) && (y >= 0);
+            cp_async8(cblk[b & (NB - 1)] + s * C::CSLOT_ELEMS, vc ? g_c : safe_c, vc);
             if (!(y & 1)) g_c += a.pitch_c;   // ceil((y+1)/2) > ceil(y/2) exactly when y is even
         }
         cp_async_commit();
@@ -234,8 +222,10 @@ struct Streamer {
     static __device__ __forceinline__ int rb_kk(int row, int t) { return (row + ((t - 1) & 1)) & 1; }
     static __device__ __forceinline__ int rb_need(int row, int t) { return rb_kk(row, t) ? 2 : 1; }
 
+    // Dirichlet ring: only rows 0 / N (rows beyond them are zero by construction) and, on
+    // strips touching the boundary, the columns flagged in cz[] ever need forcing.
     // Dirichlet columns: AND with a per-lane bit mask (all-ones in the interior; exact, NaN-safe, gives +0).
-    // Dirichlet rows 0 / N are handled by a warp-uniform test around each stage (rows beyond them are
+    // Dirichlet rows 0 / N are handled by a warp-uniform branch around each stage (rows beyond them are
     // zero by construction), so interior rows pay two logic ops per value and nothing else.
     __device__ __forceinline__ void mask_cols(T (&o)[V]) const
     {
@@ -252,27 +242,142 @@ struct Streamer {
     }
     __device__ __forceinline__ bool ring_row(int row) const { return (row <= 0) || (row >= a.N); }
 
-    // One pipeline step: row y of the input arrives.  Window positions: NEW is written in this step; P1 / P2 / P3 were
-    // written one / two / three steps ago (P3 is the same register as NEW: the oldest row, read before it is replaced).
-    // Every consumer below reads P1 / P2 / P3 only, i.e. nothing that is produced in this step.
+    // one pipeline step: row y of the input arrives
     template <int PH>
     __device__ __forceinline__ void step(int y)
     {
-        constexpr int NEW = PH, P1 = (PH + 2) % 3, P2 = (PH + 1) % 3, P3 = PH;
+        constexpr int NEW = PH, MID = (PH + 2) % 3, OLD = (PH + 1) % 3;
+        T cur[V];
+        // ---- stage 0: the incoming row (POST: plus the interpolated coarse correction) ----
+        if (ZG) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) cur[k] = (T)0;
+        } else {
+            ldv<T>(rslot<PH, 0>(), cur);
+        }
+        if (C::HAS_POST) {
+            T ca[H + 1], cb[H + 1], e[V];
+            const T* pa = cslot<PH, 0>();
+#pragma unroll
+            for (int k = 0; k < H; ++k) cb[k] = pa[k];
+            cb[H] = __shfl_down_sync(FULL, cb[0], 1);
+            if (y & 1) {  // (y parity is warp-uniform, so both branches are convergent)
+                const T* pp = cslot<PH, 1>();
+#pragma unroll
+                for (int k = 0; k < H; ++k) ca[k] = pp[k];
+                ca[H] = __shfl_down_sync(FULL, ca[0], 1);
+#pragma unroll
+                for (int k = 0; k < H; ++k) {
+                    e[2 * k] = (T)0.5 * (ca[k] + cb[k]);                                       // P:407
+                    e[2 * k + 1] = (T)0.25 * (((ca[k] + cb[k]) + ca[k + 1]) + cb[k + 1]);      // P:419
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < H; ++k) {
+                    e[2 * k] = cb[k];                                                          // P:401
+                    e[2 * k + 1] = (T)0.5 * (cb[k] + cb[k + 1]);                               // P:413
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < V; ++k) cur[k] = ring_row(y) ? (T)0 : (ZG ? e[k] : cur[k] + e[k]);   // P:623 (ZG: bare interpolation, P:645)
+            mask_cols(cur);
+        }
+        put_row<NEW>(0, cur, (RBGS && NS >= 1) ? rb_need(y, 1) : 3);
 
-        // ---- PRE: full weighting of the residual rows of the last three steps (coarse row when the centre row is even) ----
+        // ---- smoothing stages: stage s produces row y-s of u_s from the window of u_{s-1} ----
+#pragma unroll
+        for (int s = 1; s <= NS; ++s) {
+            const int rs = y - s;
+            T ff[V], o[V];
+            if (s == 1) ldv<T>(rslot<PH, 1>() + 32 * V, ff);
+            else if (s == 2) ldv<T>(rslot<PH, 2>() + 32 * V, ff);
+            else if (s == 3) ldv<T>(rslot<PH, 3>() + 32 * V, ff);
+            else ldv<T>(rslot<PH, 4>() + 32 * V, ff);
+            if (ring_row(rs)) {   // warp-uniform, rare
+#pragma unroll
+                for (int k = 0; k < V; ++k) o[k] = (T)0;
+            } else if constexpr (RBGS) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) o[k] = W[s - 1][MID][k];     // the other colour is carried over
+                if (rb_kk(rs, s) == 0) {                                 // warp-uniform (see rb_kk)
+#pragma unroll
+                    for (int k = 0; k < V; k += 2) {
+                        const T l = (k == 0) ? WL[s - 1][MID] : W[s - 1][MID][k - 1];
+                        o[k] = gs_pt<T>(ff[k], sigma4<T>(W[s - 1][OLD][k], W[s - 1][NEW][k], l, W[s - 1][MID][k + 1]));
+                        mask_col(o[k], k);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 1; k < V; k += 2) {
+                        const T r = (k == V - 1) ? WR[s - 1][MID] : W[s - 1][MID][k + 1];
+                        o[k] = gs_pt<T>(ff[k], sigma4<T>(W[s - 1][OLD][k], W[s - 1][NEW][k], W[s - 1][MID][k - 1], r));
+                        mask_col(o[k], k);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const T l = (k == 0) ? WL[s - 1][MID] : W[s - 1][MID][k - 1];
+                    const T r = (k == V - 1) ? WR[s - 1][MID] : W[s - 1][MID][k + 1];
+                    o[k] = jacobi_pt<T>(a.c0, a.c1, W[s - 1][MID][k], ff[k], sigma4<T>(W[s - 1][OLD][k], W[s - 1][NEW][k], l, r));
+                }
+                mask_cols(o);
+            }
+            if (s < C::NW) put_row<NEW>(s, o, (RBGS && s < NS) ? rb_need(rs, s + 1) : 3);
+            if (s == NS) {
+                if (lane_st && rs >= y0 && rs < y1) stv<T>(g_o, o);
+                g_o += a.pitch;
+            }
+        }
+
+        // ---- NORM: residual of the output iterate u_NS (row y-NS-1), squared and accumulated on the stored points ----
+        if constexpr (NORM) {
+            const int rr = y - NS - 1;
+            if (!ring_row(rr) && lane_st && rr >= y0 && rr < y1) {
+                T ff[V];
+                ldv<T>(rslot<PH, NS + 1>() + 32 * V, ff);
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const T l = (k == 0) ? WL[NS][MID] : W[NS][MID][k - 1];
+                    const T r = (k == V - 1) ? WR[NS][MID] : W[NS][MID][k + 1];
+                    T o = resid_pt<T>(W[NS][MID][k], ff[k], sigma4<T>(W[NS][OLD][k], W[NS][NEW][k], l, r));
+                    mask_col(o, k);
+                    nacc += (double)o * (double)o;
+                }
+            }
+        }
+
+        // ---- PRE: residual of u_NS (row y-NS-1) and full weighting (coarse row when that row is odd) ----
         if (C::HAS_PRE) {
-            const int yc = y - 2 * NS - 4;     // R[P3] = row yc-1, R[P2] = row yc (fine centre row 2I), R[P1] = row yc+1
-            if (!(yc & 1)) {
+            const int rr = y - NS - 1;
+            T ff[V], o[V];
+            ldv<T>(rslot<PH, NS + 1>() + 32 * V, ff);
+            if (ring_row(rr)) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) o[k] = (T)0;
+            } else {
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const T l = (k == 0) ? WL[NS][MID] : W[NS][MID][k - 1];
+                    const T r = (k == V - 1) ? WR[NS][MID] : W[NS][MID][k + 1];
+                    o[k] = resid_pt<T>(W[NS][MID][k], ff[k], sigma4<T>(W[NS][OLD][k], W[NS][NEW][k], l, r));
+                }
+                mask_cols(o);
+            }
+#pragma unroll
+            for (int k = 0; k < V; ++k) R[NEW][k] = o[k];
+            RL[NEW] = __shfl_up_sync(FULL, o[V - 1], 1);
+            if (rr & 1) {
+                const int yc = rr - 1;  // fine centre row 2I (MID of the residual window)
                 T oc[H];
 #pragma unroll
                 for (int j = 0; j < H; ++j) {
                     const int k = 2 * j;
-                    const T nw = (k == 0) ? RL[P3] : R[P3][k - 1];
-                    const T wv = (k == 0) ? RL[P2] : R[P2][k - 1];
-                    const T sw = (k == 0) ? RL[P1] : R[P1][k - 1];
-                    oc[j] = fw_pt<T>(a.w, nw, R[P3][k + 1], sw, R[P1][k + 1], wv, R[P2][k + 1],
-                                     R[P3][k], R[P1][k], R[P2][k]);
+                    const T nw = (k == 0) ? RL[OLD] : R[OLD][k - 1];
+                    const T wv = (k == 0) ? RL[MID] : R[MID][k - 1];
+                    const T sw = (k == 0) ? RL[NEW] : R[NEW][k - 1];
+                    oc[j] = fw_pt<T>(a.w, nw, R[OLD][k + 1], sw, R[NEW][k + 1], wv, R[MID][k + 1],
+                                     R[OLD][k], R[NEW][k], R[MID][k]);
                 }
                 {   // coarse ring columns: J = 0 <=> fine column 0, J >= Nc <=> fine column >= N (same mask)
                     T tmp[V];
@@ -294,132 +399,14 @@ struct Streamer {
                 }
             }
         }
-
-        // ---- residual of u_NS, row y-2NS-2 (centre W[NS][P2]): PRE keeps it for the restriction, NORM squares it ----
-        if constexpr (C::HAS_RES) {
-            const int rr = y - 2 * NS - 2;
-            T ff[V], o[V];
-            ldv<T>(fslot<PH, 2 * NS + 2>(), ff);
-            if (ring_row(rr)) {
-#pragma unroll
-                for (int k = 0; k < V; ++k) o[k] = (T)0;
-            } else {
-#pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    const T l = (k == 0) ? WL[NS][P2] : W[NS][P2][k - 1];
-                    const T r = (k == V - 1) ? WR[NS][P2] : W[NS][P2][k + 1];
-                    o[k] = resid_pt<T>(W[NS][P2][k], ff[k], sigma4<T>(W[NS][P3][k], W[NS][P1][k], l, r));
-                }
-                mask_cols(o);
-            }
-            if constexpr (C::HAS_PRE) {
-#pragma unroll
-                for (int k = 0; k < V; ++k) R[NEW][k] = o[k];
-                RL[NEW] = __shfl_up_sync(FULL, o[V - 1], 1);
-            }
-            if constexpr (NORM) {
-                if (lane_st && rr >= y0 && rr < y1) {
-#pragma unroll
-                    for (int k = 0; k < V; ++k) nacc += (double)o[k] * (double)o[k];
-                }
-            }
-        }
-
-        // ---- smoothing stages, last first: stage s produces row y-2s of u_s from the window of u_(s-1) ----
-#pragma unroll
-        for (int s = NS; s >= 1; --s) {
-            const int rs = y - 2 * s;
-            T ff[V], o[V];
-            if (s == 1) ldv<T>(fslot<PH, 2>(), ff);
-            else if (s == 2) ldv<T>(fslot<PH, 4>(), ff);
-            else if (s == 3) ldv<T>(fslot<PH, 6>(), ff);
-            else ldv<T>(fslot<PH, 8>(), ff);
-            if (ring_row(rs)) {   // warp-uniform, rare
-#pragma unroll
-                for (int k = 0; k < V; ++k) o[k] = (T)0;
-            } else if constexpr (RBGS) {
-#pragma unroll
-                for (int k = 0; k < V; ++k) o[k] = W[s - 1][P2][k];      // the other colour is carried over
-                if (rb_kk(rs, s) == 0) {                                 // warp-uniform (see rb_kk)
-#pragma unroll
-                    for (int k = 0; k < V; k += 2) {
-                        const T l = (k == 0) ? WL[s - 1][P2] : W[s - 1][P2][k - 1];
-                        o[k] = gs_pt<T>(ff[k], sigma4<T>(W[s - 1][P3][k], W[s - 1][P1][k], l, W[s - 1][P2][k + 1]));
-                        mask_col(o[k], k);
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 1; k < V; k += 2) {
-                        const T r = (k == V - 1) ? WR[s - 1][P2] : W[s - 1][P2][k + 1];
-                        o[k] = gs_pt<T>(ff[k], sigma4<T>(W[s - 1][P3][k], W[s - 1][P1][k], W[s - 1][P2][k - 1], r));
-                        mask_col(o[k], k);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    const T l = (k == 0) ? WL[s - 1][P2] : W[s - 1][P2][k - 1];
-                    const T r = (k == V - 1) ? WR[s - 1][P2] : W[s - 1][P2][k + 1];
-                    o[k] = jacobi_pt<T>(a.c0, a.c1, W[s - 1][P2][k], ff[k], sigma4<T>(W[s - 1][P3][k], W[s - 1][P1][k], l, r));
-                }
-                mask_cols(o);
-            }
-            if (s < C::NW) put_row<NEW>(s, o, (RBGS && s < NS) ? rb_need(rs, s + 1) : 3);
-            if (s == NS) {
-                if (lane_st && rs >= y0 && rs < y1) stv<T>(g_o, o);
-                g_o += a.pitch;
-            }
-        }
-
-        // ---- stage 0: the incoming row (POST: plus the interpolated coarse correction) ----
-        {
-            T cur[V];
-            if (ZG) {
-#pragma unroll
-                for (int k = 0; k < V; ++k) cur[k] = (T)0;
-            } else {
-                ldv<T>(uslot<PH>(), cur);
-            }
-            if (C::HAS_POST) {
-                T ca[H + 1], cb[H + 1], e[V];
-                const T* pa = cslot<PH, 0>();
-#pragma unroll
-                for (int k = 0; k < H; ++k) cb[k] = pa[k];
-                cb[H] = __shfl_down_sync(FULL, cb[0], 1);
-                if (y & 1) {  // (y parity is warp-uniform, so both branches are convergent)
-                    const T* pp = cslot<PH, 1>();
-#pragma unroll
-                    for (int k = 0; k < H; ++k) ca[k] = pp[k];
-                    ca[H] = __shfl_down_sync(FULL, ca[0], 1);
-#pragma unroll
-                    for (int k = 0; k < H; ++k) {
-                        e[2 * k] = (T)0.5 * (ca[k] + cb[k]);                                       // P:407
-                        e[2 * k + 1] = (T)0.25 * (((ca[k] + cb[k]) + ca[k + 1]) + cb[k + 1]);      // P:419
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < H; ++k) {
-                        e[2 * k] = cb[k];                                                          // P:401
-                        e[2 * k + 1] = (T)0.5 * (cb[k] + cb[k + 1]);                               // P:413
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < V; ++k) cur[k] = ring_row(y) ? (T)0 : (ZG ? e[k] : cur[k] + e[k]);   // P:623 (ZG: bare interpolation, P:645)
-                mask_cols(cur);
-            }
-            put_row<NEW>(0, cur, (RBGS && NS >= 1) ? rb_need(y, 1) : 3);
-        }
     }
 
     __device__ __forceinline__ void set_blocks(int q)
     {
 #pragma unroll
-        for (int j = 0; j < NBU; ++j) ublk[j] = uring + ((q + j) & (NBU - 1)) * BLK;
-#pragma unroll
-        for (int j = 0; j < NBF; ++j) fblk[j] = fring + ((q + j) & (NBF - 1)) * BLK;
-        if (C::HAS_POST) {
-#pragma unroll
-            for (int j = 0; j < NBC; ++j) cblk[j] = cring + ((q + j) & (NBC - 1)) * CBLK;
+        for (int j = 0; j < NB; ++j) {
+            blk[j] = ring + ((q + j) & (NB - 1)) * BLK;
+            if (C::HAS_POST) cblk[j] = cring + ((q + j) & (NB - 1)) * CBLK;
         }
     }
 
@@ -434,12 +421,9 @@ struct Streamer {
         const int out_hi = X0 + V * C::HLANES + C::OUTW;
         y0 = a.ya + chunk * a.ry;
         y1 = min(y0 + a.ry, a.yb);
-        T* wbase = ring_base + (size_t)warp * C::WARP_ELEMS;
-        uring = wbase + lane * V;
-        fring = wbase + C::U_ELEMS + lane * V;
-        cring = wbase + C::U_ELEMS + C::F_ELEMS + lane * H;
-        const int ylo = y0 - C::HT, yhi = y1 - 1 + C::DRAIN;
-        y_need = y1 - 1 + C::HB;
+        ring = ring_base + (size_t)warp * C::WARP_ELEMS + lane * V;
+        cring = ring_base + (size_t)warp * C::WARP_ELEMS + C::DEPTH * C::SLOT_ELEMS + lane * H;
+        const int ylo = y0 - C::HT, yhi = y1 - 1 + C::HB;
         lane_ld = (c < a.pitch) && !dead;
         lane_ldc = ((c >> 1) < a.pitch_c) && !dead;
         lane_st = (c >= out_lo) && (c < out_hi) && (c < a.N) && !dead;
@@ -462,18 +446,10 @@ struct Streamer {
             RL[p] = (T)0;
         }
         nacc = 0.0;
-        // the f ring is read up to FBACK steps behind the prefetch front: slots not yet filled in the first steps must
-        // hold finite values (they only feed rows that are never stored, but NaNs would be slow paths for nothing)
-        for (int i = C::D; i < 3 * NBF; ++i) {   // (slots 0 .. D-1 are the prologue's)
-            T z[V];
-#pragma unroll
-            for (int k = 0; k < V; ++k) z[k] = (T)0;
-            stv<T>(fring + i * C::SLOT_ELEMS, z);
-        }
 
         g_u = a.u_in + (i64)ylo * a.pitch + c;
         g_f = a.f + (i64)ylo * a.pitch + c;
-        g_o = a.u_out + (i64)(ylo - 2 * NS) * a.pitch + c;   // row produced by stage NS in the first step
+        g_o = a.u_out + (i64)(ylo - NS) * a.pitch + c;   // row produced by stage NS in the first step
         safe_u = a.u_in + (i64)a.row_lo * a.pitch;
         safe_f = a.f + (i64)a.row_lo * a.pitch;
         safe_c = a.ec;
@@ -498,7 +474,7 @@ struct Streamer {
             issue<C::D + 2>(y + 2 + C::D);
             wait_row<2>();
             step<2>(y + 2);
-            ++q;
+            q = (q + 1) & (NB - 1);
         }
         cp_async_wait<0>();
     }
