@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstddef>
 #include <cstring>
 #include <thread>
 
@@ -226,6 +227,14 @@ void Ctx::release() noexcept
         if (stager.ev_main) cudaEventDestroy(stager.ev_main);
         stager = Stager();
     }
+    for (auto& kv : solve_graphs)
+        if (kv.second.first) cudaGraphExecDestroy(kv.second.first);
+    solve_graphs.clear();
+    if (d_solve_ctl) cudaFree(d_solve_ctl);
+    d_solve_ctl = nullptr;
+    solve_ctl_cap = 0;
+    if (body_stream) cudaStreamDestroy(body_stream);
+    body_stream = nullptr;
     if (d_partials) cudaFree(d_partials);
     if (d_dst_S) cudaFree(d_dst_S);
     if (d_dst_d) cudaFree(d_dst_d);
@@ -752,6 +761,151 @@ double Ctx::read_norm(const Level& lv)
     return std::sqrt(sumsq);
 }
 
+// ---------------------------------------------------------------------------------
+// The tolerance loop as one graph launch (single GPU).  The host loop below pays a read-back, a host decision and a
+// graph launch between two cycles (~40 us of idle GPU at 4097^2).  Here the decision is taken on the device: a CUDA
+// graph with a conditional WHILE node whose body is one cycle (its last kernel leaves sum r^2 in d_norm) followed by
+// k_solve_check, which records ||r_k||, decides `continue` and sets the node's condition.  The first cycle is peeled in
+// front of the node, because the host-side buffer parities after the first cycle may differ from those it started from;
+// from the second cycle on they must be a fixed point (checked at capture time, else the host loop runs).
+// ---------------------------------------------------------------------------------
+#ifndef MGB_EMU
+struct SolveCtl {
+    double r0, rtol;
+    int k, max_cycles;
+    double hist[1];   // hist[0 .. max_cycles]
+};
+
+static __global__ void k_solve_check(cudaGraphConditionalHandle h, const double* __restrict__ sumsq, SolveCtl* __restrict__ c)
+{
+    if (threadIdx.x == 0) {
+        const double rk = sqrt(*sumsq);
+        const int k = ++c->k;
+        c->hist[k] = rk;
+        const bool done = (c->r0 == 0.0) || (rk <= c->rtol * c->r0) || (k >= c->max_cycles);
+        cudaGraphSetConditional(h, done ? 0u : 1u);
+    }
+}
+
+bool Ctx::solve_device_loop(double rtol, int max_cycles, int nu1, int nu2, int gamma, double r0, int* k_out, double* history)
+{
+    if (solve_loop_mode < 0) {
+        const char* e = getenv("MGB200_SOLVE_GRAPH");
+        solve_loop_mode = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (solve_loop_mode != 1 || cfg.world != 1 || !(cfg.flags & MG_GRAPH) || !(cfg.flags & MG_FUSED) || capturing ||
+        max_cycles < 1 || max_cycles > 100000)
+        return false;
+    const int top = cfg.finest_level;
+    if (solve_ctl_cap < max_cycles) {
+        if (d_solve_ctl) MG_CK(cudaFree(d_solve_ctl));
+        d_solve_ctl = nullptr;
+        MG_CK(cudaMalloc(&d_solve_ctl, sizeof(SolveCtl) + sizeof(double) * (size_t)(max_cycles + 1)));
+        solve_ctl_cap = max_cycles;
+    }
+    SolveCtl* ctl = (SolveCtl*)d_solve_ctl;
+    if (!body_stream) MG_CK(cudaStreamCreateWithFlags(&body_stream, cudaStreamNonBlocking));
+
+    const std::string s0 = state_blob();
+    auto key = std::make_tuple(top, nu1, nu2, gamma, s0);
+    auto it = solve_graphs.find(key);
+    if (it == solve_graphs.end()) {
+        fused_pretune(*this, top, nu1, nu2, gamma);
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        std::string s1, s2;
+        bool ok = true;
+        cudaStream_t main_stream = stream;
+        auto one_cycle = [&](cudaGraphConditionalHandle h) {
+            want_post_norm = true;
+            post_norm_done = false;
+            cycle_rec_visits(top, nu1, nu2, gamma, 1);
+            want_post_norm = false;
+            if (!post_norm_done) ok = false;
+            k_solve_check<<<1, 32, 0, stream>>>(h, d_norm, ctl);
+            ++lc.n;
+        };
+        const long long launches_before = lc.n;
+        try {
+            MG_CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            capturing = true;
+            cudaStreamCaptureStatus st;
+            const cudaGraphNode_t* deps = nullptr;
+            size_t ndeps = 0;
+            MG_CK(cudaStreamGetCaptureInfo(stream, &st, nullptr, &g, &deps, &ndeps));
+            cudaGraphConditionalHandle h;
+            MG_CK(cudaGraphConditionalHandleCreate(&h, g, 0, cudaGraphCondAssignDefault));
+            one_cycle(h);                                      // peeled first cycle: s0 -> s1
+            s1 = state_blob();
+            MG_CK(cudaStreamGetCaptureInfo(stream, &st, nullptr, &g, &deps, &ndeps));
+            cudaGraphNodeParams np = {};
+            np.type = cudaGraphNodeTypeConditional;
+            np.conditional.handle = h;
+            np.conditional.type = cudaGraphCondTypeWhile;
+            np.conditional.size = 1;
+            cudaGraphNode_t node;
+            MG_CK(cudaGraphAddNode(&node, g, deps, ndeps, &np));
+            cudaGraph_t body = np.conditional.phGraph_out[0];
+            MG_CK(cudaStreamUpdateCaptureDependencies(stream, &node, 1, cudaStreamSetCaptureDependencies));
+            MG_CK(cudaStreamEndCapture(stream, &g));
+            // the body: one cycle from s1, which must lead back to s1
+            MG_CK(cudaStreamBeginCaptureToGraph(body_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+            stream = body_stream;
+            one_cycle(h);
+            s2 = state_blob();
+            stream = main_stream;
+            cudaGraph_t same = nullptr;
+            MG_CK(cudaStreamEndCapture(body_stream, &same));
+            capturing = false;
+            if (s2 != s1) ok = false;
+            if (ok) MG_CK(cudaGraphInstantiate(&exec, g, 0));
+        } catch (...) {
+            // leave no capture open, then fall back to the host loop for the life of this context
+            stream = main_stream;
+            capturing = false;
+            want_post_norm = false;
+            cudaGraph_t junk = nullptr;
+            cudaStreamCaptureStatus st;
+            if (cudaStreamIsCapturing(body_stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) cudaStreamEndCapture(body_stream, &junk);
+            if (cudaStreamIsCapturing(main_stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) cudaStreamEndCapture(main_stream, &junk);
+            cudaGetLastError();
+            ok = false;
+        }
+        if (g) cudaGraphDestroy(g);
+        lc.n = launches_before;
+        set_state(s0);
+        if (!ok) {
+            if (exec) cudaGraphExecDestroy(exec);
+            solve_loop_mode = 0;
+            return false;
+        }
+        it = solve_graphs.emplace(key, std::make_pair(exec, s1)).first;
+    }
+    SolveCtl head;
+    head.r0 = r0;
+    head.rtol = rtol;
+    head.k = 0;
+    head.max_cycles = max_cycles;
+    head.hist[0] = r0;
+    MG_CK(cudaMemcpyAsync(ctl, &head, sizeof(SolveCtl), cudaMemcpyHostToDevice, stream));
+    MG_CK(cudaGraphLaunch(it->second.first, stream));
+    ++graph_launches;
+    std::vector<double> hist((size_t)max_cycles + 1);
+    SolveCtl tail;
+    MG_CK(cudaMemcpyAsync(&tail, ctl, sizeof(SolveCtl), cudaMemcpyDeviceToHost, stream));
+    MG_CK(cudaMemcpyAsync(hist.data(), (char*)ctl + offsetof(SolveCtl, hist), sizeof(double) * hist.size(), cudaMemcpyDeviceToHost, stream));
+    MG_CK(cudaStreamSynchronize(stream));
+    set_state(it->second.second);
+    *k_out = tail.k;
+    if (history)
+        for (int i = 0; i <= tail.k; ++i) history[i] = hist[i];
+    history_last = hist[tail.k];
+    return true;
+}
+#else
+bool Ctx::solve_device_loop(double, int, int, int, int, double, int*, double*) { return false; }
+#endif
+
 // Tolerance-controlled loop (the reference runs a fixed count, P:635).  The norm after each cycle comes out
 // of the cycle's own last kernel on the finest level when the fused POST applies (k_stream_norm: no extra pass over the
 // grid); otherwise from a residual pass without the store.
@@ -762,6 +916,11 @@ int Ctx::solve(double rtol, int max_cycles, int nu1, int nu2, int gamma, double*
     if (history) history[0] = r0;
     int k = 0;
     double rk = r0;
+    if (r0 > 0.0 && solve_device_loop(rtol, max_cycles, nu1, nu2, gamma, r0, &k, history)) {
+        rk = history_last;
+        if (relres) *relres = rk / r0;
+        return k;
+    }
     while (k < max_cycles) {
         want_post_norm = true;
         post_norm_done = false;

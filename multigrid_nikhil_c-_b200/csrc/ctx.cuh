@@ -168,6 +168,13 @@ struct Ctx {
 
     // data movement
     enum Which { W_U = 0, W_F = 1, W_R = 2 };
+    // device-loop solve (ctx.cu: solve_device_loop): control block, body-capture stream, cached graphs
+    void* d_solve_ctl = nullptr;
+    int solve_ctl_cap = 0;
+    cudaStream_t body_stream = nullptr;
+    std::map<std::tuple<int, int, int, int, std::string>, std::pair<cudaGraphExec_t, std::string>> solve_graphs;
+    double history_last = 0.0;
+    int solve_loop_mode = -1;   // -1: read MGB200_SOLVE_GRAPH on first use; 0 host loop; 1 device loop
     Stager stager;
     void stager_init();
     // rows [ya, yb) of a padded device array <-> the same rows of an n x n host vector in ordinary (pageable) memory
@@ -197,6 +204,8 @@ struct Ctx {
     int solve(double rtol, int max_cycles, int nu1, int nu2, int gamma, double* relres, double* history);
     float time_op(int op, int level, int reps);
     double read_norm(const Level& lv);
+    // the whole tolerance loop as ONE graph launch: a conditional WHILE node whose body is the cycle (device-side decision)
+    bool solve_device_loop(double rtol, int max_cycles, int nu1, int nu2, int gamma, double r0, int* k_out, double* history);
 
     void sync();
     void ensure_halo(Level& lv, Which w, int depth);

@@ -349,6 +349,28 @@ def test_exact_coarsest_solve_restores_the_textbook_rate_at_the_reference_depth(
     assert abs(h1[-1] / h1[-2] - f_exact) < 0.05
 
 
+@pytest.mark.parametrize("level,smoother,gamma", [(8, "jacobi", 1), (8, "rbgs", 1), (9, "jacobi", 2), (10, "jacobi", 1), (5, "jacobi", 1)])
+def test_solve_as_one_device_side_loop(mgb, orc, knob, level, smoother, gamma):
+    """MGB200_SOLVE_GRAPH=1: the tolerance loop is ONE graph launch (conditional WHILE node, the decision taken by a kernel).
+    Same cycle count, same history, same iterate as the host loop and the oracle; a second solve reuses the graph; hitting
+    max_cycles stops the loop too.  (On a level that has no fused POST the call silently uses the host loop.)"""
+    p = oracle.Params(smoother=1 if smoother == "rbgs" else 0, gamma=gamma, nthreads=4)
+    knob("MGB200_SOLVE_GRAPH", "1")
+    with make(mgb, level, smoother=smoother) as mg:
+        b = mg.globalforcefunction(4.0)
+        for max_cycles in (60, 3, 60):
+            mg.zero_u(level)
+            g0 = mg.info(mgb.capi.MG_INFO_GRAPH_LAUNCHES)
+            k, rel, hist = mg.solve(1e-8, max_cycles, 2, 2, gamma)
+            u, ko, ho = orc.solve(np.zeros_like(b), b, 1e-8, max_cycles, p)
+            assert k == ko and np.allclose(hist, ho, rtol=1e-10, atol=0)
+            assert_bitwise(mg.get_u(level), u, f"solution, max_cycles={max_cycles}")
+            if level >= 8:
+                assert mg.info(mgb.capi.MG_INFO_GRAPH_LAUNCHES) - g0 == 1, "the whole solve must be one graph launch"
+        mg.cycle(level, 2, 2, gamma)                     # ordinary calls still work on the state the loop left
+        assert_bitwise(mg.get_u(level), orc.vcyclemultigrid(u, b, p), "cycle after a device-loop solve")
+
+
 def test_golden_fixtures(mgb):
     """Committed oracle outputs (tests/golden/oracle_golden.npz, made by make_golden.py)."""
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.npz"))
