@@ -790,8 +790,8 @@ static __global__ void k_solve_check(cudaGraphConditionalHandle h, const double*
 bool Ctx::solve_device_loop(double rtol, int max_cycles, int nu1, int nu2, int gamma, double r0, int* k_out, double* history)
 {
     if (solve_loop_mode < 0) {
-        const char* e = getenv("MGB200_SOLVE_GRAPH");
-        solve_loop_mode = (e && e[0] == '1') ? 1 : 0;
+        const char* e = getenv("MGB200_SOLVE_GRAPH");     // on by default (verified on the B200); "0" = host loop
+        solve_loop_mode = (e && e[0] == '0') ? 0 : 1;
     }
     if (solve_loop_mode != 1 || cfg.world != 1 || !(cfg.flags & MG_GRAPH) || !(cfg.flags & MG_FUSED) || capturing ||
         max_cycles < 1 || max_cycles > 100000)

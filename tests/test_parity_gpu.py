@@ -351,11 +351,16 @@ def test_exact_coarsest_solve_restores_the_textbook_rate_at_the_reference_depth(
 
 @pytest.mark.parametrize("level,smoother,gamma", [(8, "jacobi", 1), (8, "rbgs", 1), (9, "jacobi", 2), (10, "jacobi", 1), (5, "jacobi", 1)])
 def test_solve_as_one_device_side_loop(mgb, orc, knob, level, smoother, gamma):
-    """MGB200_SOLVE_GRAPH=1: the tolerance loop is ONE graph launch (conditional WHILE node, the decision taken by a kernel).
+    """Default on one GPU (MGB200_SOLVE_GRAPH=0 selects the host loop): the tolerance loop is ONE graph launch (conditional WHILE node, the decision taken by a kernel).
     Same cycle count, same history, same iterate as the host loop and the oracle; a second solve reuses the graph; hitting
     max_cycles stops the loop too.  (On a level that has no fused POST the call silently uses the host loop.)"""
     p = oracle.Params(smoother=1 if smoother == "rbgs" else 0, gamma=gamma, nthreads=4)
     knob("MGB200_SOLVE_GRAPH", "1")
+    with make(mgb, level, smoother=smoother, graph=False) as mg0:      # without MG_GRAPH: the host loop
+        mg0.force_constant(4.0)
+        mg0.zero_u(level)
+        k0, _, h0 = mg0.solve(1e-8, 60, 2, 2, gamma)
+        u0 = mg0.get_u(level)
     with make(mgb, level, smoother=smoother) as mg:
         b = mg.globalforcefunction(4.0)
         for max_cycles in (60, 3, 60):
@@ -365,6 +370,9 @@ def test_solve_as_one_device_side_loop(mgb, orc, knob, level, smoother, gamma):
             u, ko, ho = orc.solve(np.zeros_like(b), b, 1e-8, max_cycles, p)
             assert k == ko and np.allclose(hist, ho, rtol=1e-10, atol=0)
             assert_bitwise(mg.get_u(level), u, f"solution, max_cycles={max_cycles}")
+            if max_cycles == 60:
+                assert k == k0 and np.allclose(hist, h0, rtol=1e-12, atol=0)
+                assert_bitwise(mg.get_u(level), u0, "device loop vs host loop")
             if level >= 8:
                 assert mg.info(mgb.capi.MG_INFO_GRAPH_LAUNCHES) - g0 == 1, "the whole solve must be one graph launch"
         mg.cycle(level, 2, 2, gamma)                     # ordinary calls still work on the state the loop left
