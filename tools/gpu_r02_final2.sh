@@ -3,7 +3,7 @@
 set -u
 N=${1:-4}
 mkdir -p gpurun_out; O=gpurun_out
-timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29547 bench.py --gpus $N --steps 20 --warmup 5 > $O/r02_final_bench_n$N.json 2> $O/r02_final_bench_n$N.err
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29547 bench.py --gpus $N --steps 20 --warmup 5 > $O/r02_final_bench_n$N.json 2> $O/r02_final_bench_n$N.err
 echo "rc=$?"
 python - $N <<'PY'
 import json, sys
