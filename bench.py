@@ -478,19 +478,33 @@ def run_ours(args, rank, world, local_rank):
     # cycle, profiles/*launches*), else the plain sweep.  The plain smoother numbers are kept under "smoother".
     dom = pre_key if (pre_key in kernels and not args.no_fused) else "smoother_sweep"
     ns = (4 if rb else 2)
-    kname = (f"k_stream<{'double' if esize == 8 else 'float'},{ns},PRE,{'rbgs' if rb else 'jacobi'}> (2 {'red-black GS' if rb else 'Jacobi'} "
+    tname = 'double' if esize == 8 else 'float'
+    kname = (f"k_stream<{tname},{ns},PRE,{'rbgs' if rb else 'jacobi'}> (2 {'red-black GS' if rb else 'Jacobi'} "
              f"sweeps + residual + full weighting, finest level)") if dom == pre_key else "k_jacobi / k_rbgs (one sweep, finest level)"
+    # K consecutive cycles with visit chains: the one big launch per cycle on the finest level is the POST+PRE chain
+    # kernel (PRE and POST run once per K cycles), provided the cycle's sweep counts are the ones the chain fuses
+    chain_used = (chain_key in kernels and K > 1 and os.environ.get("MGB200_CHAIN") != "0" and not args.no_fused and
+                  ((not rb and nu1 == 2 and nu2 == 2) or (rb and nu1 == 1 and nu2 == 1)))
+    if chain_used:
+        dom = chain_key
+        kname = (f"k_stream_chain<{tname},4,{'rbgs' if rb else 'jacobi'}> (prolongation + correction + nu2+nu1 sweeps + residual + "
+                 f"full weighting in one launch, finest level; replaces POST + PRE = 6.5 S bytes per point by 3.5 S)")
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(f"{'pre' if dom == pre_key else 'sweep'}_{smoother}_L{level}_{args.dtype}_n{world}")
+            traffic = json.load(open(tpath)).get(f"{'chain' if dom == chain_key else ('pre' if dom == pre_key else 'sweep')}_{smoother}_L{level}_{args.dtype}_n{world}")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["GBps"] / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
                 "ms_per_launch": kernels[dom]["ms"], "rows_per_rank": own_rows,
+                "share_of_step": kernels[dom]["ms"] / ms_step,
+                "two_launch_equivalent": ({"bytes": 6.5 * esize * pts, "GBps": 6.5 * esize * pts / (kernels[dom]["ms"] * 1e-3) / 1e9,
+                                           "frac": 6.5 * esize * pts / (kernels[dom]["ms"] * 1e-3) / 1e9 / peak,
+                                           "note": "the chain kernel does the work of POST + PRE (6.5 S algorithmic bytes in two launches)"}
+                                          if chain_used else None),
                 "smoother": {k: kernels[k] for k in ("smoother_sweep", "two_sweeps_one_launch") if k in kernels},
                 "kernels": kernels, "cycle_ms_from_level_down": level_ms}
 
