@@ -114,7 +114,7 @@ int mg_prolong_set(mg_ctx* ctx, int fine_level);                   /* bare inter
 int mg_cycle(mg_ctx* ctx, int level, int nu1, int nu2, int gamma); /* vcyclemultigrid P:575-627; gamma=2 => W */
 /* `count` consecutive cycles on the same right-hand side == the loop P:646-648 (`for i <= mu0: vec_h = vcyclemultigrid(...)`).
  * Same result as `count` mg_cycle calls, bit for bit; lets the library keep the iterate on chip between the post-smoothing
- * of one cycle and the pre-smoothing of the next (MGB200_CHAIN=1, opt-in) and replay the whole run as one CUDA graph. */
+ * of one cycle and the pre-smoothing of the next (visit chains, the default) and replay the whole run as one CUDA graph. */
 int mg_cycles(mg_ctx* ctx, int level, int nu1, int nu2, int gamma, int count);
 int mg_fmg(mg_ctx* ctx, int cycles_per_level, int nu1, int nu2);   /* fullmultigrid P:629-650 (reference cycles = mu0+1) */
 int mg_solve(mg_ctx* ctx, double rtol, int max_cycles, int nu1, int nu2, int gamma,

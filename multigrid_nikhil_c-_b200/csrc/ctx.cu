@@ -91,7 +91,7 @@ void Ctx::init()
 
     levels.resize(cfg.finest_level + 1);
     // stored halo rows per level: kHaloRows covers every fused kernel; the communication-avoiding schedule
-    // (opt-in) computes rows beyond the slab and needs deeper halos on the fine levels (sched.h)
+    // (the default) computes rows beyond the slab and needs deeper halos on the fine levels (sched.h)
     int halo_rows[32];
     for (int l = 0; l < 32; ++l) halo_rows[l] = kHaloRows;
     if (cfg.world > 1) {

@@ -308,7 +308,7 @@ template int fused_jacobi<double>(Ctx&, Level&, int, double, double);
 template int fused_jacobi<float>(Ctx&, Level&, int, float, float);
 
 // ---------------------------------------------------------------------------------
-// zero-guess chain (opt-in MGB200_ZERO_GUESS=1): PRE(l) does not write the zero coarse guess when the first
+// zero-guess chain (default; MGB200_ZERO_GUESS=0 turns it off): PRE(l) does not write the zero coarse guess when the first
 // kernel of level l-1 is a zero-guess variant that does not read u either (the stream PRE or the tail).
 // Saves S/4 bytes per fine point in PRE(l) and S per point in PRE(l-1).  Any other reader of a logically-zero
 // iterate goes through Ctx::materialize_u, so a wrong prediction costs time, never correctness.
@@ -368,7 +368,7 @@ static void pre_fused(Ctx& ctx, Level& lv, Level& lcv, int nu1)
         ctx.materialize_u(lv);
     }
     if (ctx.zero_guess && !lv.distributed) {
-        // opt-in zero-guess chain
+        // zero-guess chain
         const bool wz = !child_takes_zero_guess(ctx, lv, nu1);
         if (lv.u_zero && nu1 == k) {
             if (!rb) {
@@ -462,7 +462,7 @@ static void post_fused(Ctx& ctx, Level& lv, Level& lcv, int nu2)
 }
 
 // ---------------------------------------------------------------------------------
-// visit chains (opt-in MGB200_CHAIN=1): when a level is visited several times in a row on the same right-hand
+// visit chains (default; MGB200_CHAIN=0 turns them off): when a level is visited several times in a row on the same right-hand
 // side -- consecutive cycles on the top level (fullmultigrid runs mu0+1 per level, P:646-648; mg_cycles), the gamma
 // visits of a W-cycle on every level below -- POST of visit v and PRE of visit v+1 are ONE streaming launch
 // (stream.cuh MODE_POSTPRE): 3.5 S bytes per point instead of 6.5 S, the iterate between them never goes to memory.
@@ -600,7 +600,7 @@ static void run_tail(Ctx& ctx, int level, int nu1, int nu2, int gamma)
 }
 
 // ---------------------------------------------------------------------------------
-// communication-avoiding V-cycle over the distributed levels (sched.h), opt-in MGB200_COMM_AVOID=1.
+// communication-avoiding V-cycle over the distributed levels (sched.h), the default at world > 1 (MGB200_COMM_AVOID=0: lazy exchanges).
 // The op list comes from the same planner the CPU emulation test executes with the oracle.
 // ---------------------------------------------------------------------------------
 template <typename T, int NS, int MODE, bool RBGS>

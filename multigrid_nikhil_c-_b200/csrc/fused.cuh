@@ -14,7 +14,7 @@ bool fused_rbgs(Ctx& ctx, Level& lv, int nu);
 // run one whole cycle visit of `level` with fused kernels; false = caller runs the unfused sequence
 bool fused_cycle_level(Ctx& ctx, int level, int nu1, int nu2, int gamma);
 // `visits` (>= 2) consecutive visits of `level` with POST of visit v and PRE of visit v+1 fused into one POSTPRE launch
-// (opt-in MGB200_CHAIN=1); false = not applicable here, the caller runs the visits one by one
+// (default; MGB200_CHAIN=0 turns it off); false = not applicable here, the caller runs the visits one by one
 bool fused_cycle_chain(Ctx& ctx, int level, int nu1, int nu2, int gamma, int visits);
 // choose chunk heights for the big levels before a cycle graph is captured
 void fused_pretune(Ctx& ctx, int level, int nu1, int nu2, int gamma);

@@ -48,10 +48,11 @@ constexpr bool mode_has_pre(int m) { return m == MODE_PRE || m == MODE_POSTPRE; 
 
 constexpr int kStreamWarps = 1;  // warps (independent work items) per CTA.  4 lock-stepped warps per CTA (bar.sync every 3 rows)
                                  // were measured slower and more erratic (profiles/r01_tune_stream.txt)
-// ring slots per warp: NB blocks of 3 slots, NB a power of two.  12 slots prefetch D = 9 - NS rows ahead; the deep ring
-// (24 slots, D = 21 - NS) keeps more bytes in flight per warp at the price of fewer resident warps (shared memory).
+// ring slots per warp: NB blocks of 3 slots, NB a power of two.  12 slots prefetch D = 9 - NS rows ahead.  A 24-slot ring
+// (D = 21 - NS, 8 resident warps per SM instead of 12) was measured on the B200 and is slower for every kernel
+// (profiles/r02_kernel_experiments.md); the build-time switch stays for re-measuring on other parts.
 #ifndef MGB_DEEP_RING_MIN_NS
-#define MGB_DEEP_RING_MIN_NS 99   // kernels with NS >= this use the deep ring (build-time experiment switch)
+#define MGB_DEEP_RING_MIN_NS 99   // kernels with NS >= this would use the 24-slot ring
 #endif
 constexpr int ring_slots(int ns) { return ns >= MGB_DEEP_RING_MIN_NS ? 24 : 12; }
 
@@ -531,7 +532,7 @@ k_stream_norm(const StreamArgs<T> a, double* __restrict__ partials)
     if ((threadIdx.x & 31) == 0) partials[item] = acc;
 }
 
-// POSTPRE (visit chains, opt-in MGB200_CHAIN=1) needs ~142 registers at NS = 4: its own entry point with a launch bound
+// POSTPRE (visit chains) needs ~142 registers at NS = 4: its own entry point with a launch bound
 // of 12 resident CTAs per SM (the occupancy the host caps the streaming kernels at anyway) instead of 16 => no spills
 constexpr int kStreamChainMinCtas = 12;
 template <typename T, int NS, bool RBGS>
@@ -562,8 +563,7 @@ k_stream_fmg_entry(const StreamArgs<T> a)
     st.run(reinterpret_cast<T*>(stream_smem), warp, threadIdx.x & 31, item);
 }
 
-// zero-guess variant of the PRE kernel (opt-in, MGB200_ZERO_GUESS=1): a separate kernel so that k_stream itself
-// stays byte-identical to the GPU-verified build
+// zero-guess variant of the PRE kernel (zero-guess chain): its own entry point, so that k_stream keeps its code
 template <typename T, int NS, bool RBGS>
 __global__ void __launch_bounds__(kStreamWarps * 32, kStreamMinCtas / kStreamWarps)
 k_stream_pre_zg(const StreamArgs<T> a)

@@ -252,8 +252,8 @@ k_tail(const TailArgs<T> a)
     }
 }
 
-// zero-guess variant (opt-in, MGB200_ZERO_GUESS=1): u of the top level is known to be zero and is not read.
-// A separate kernel so that k_tail stays byte-identical to the GPU-verified build.
+// zero-guess variant (zero-guess chain): u of the top level is known to be zero and is not read.
+// Its own entry point: the kernel neither loads nor waits for u of the top level.
 template <typename T, bool RBGS>
 __global__ void __launch_bounds__(kTailThreads, 1)   // one CTA per SM: 64 registers per thread (the default heuristic caps at 32 and spills)
 k_tail_zg(const TailArgs<T> a)

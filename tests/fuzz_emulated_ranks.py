@@ -1,5 +1,5 @@
 """Randomised multi-rank parity check on the CPU emulation build: random levels, agglomeration levels, smoothers, sweep
-counts, cycle index, opt-in knobs and call sequences on row slabs, every rank's rows against the single-domain oracle.
+counts, cycle index, schedule knobs and call sequences on row slabs, every rank's rows against the single-domain oracle.
     MGB200_EMU_DIR=/tmp/x python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 \
         --master-port <free> tests/fuzz_emulated_ranks.py [seconds] [seed]
 TEST TOOLING (every rank draws the same random numbers)."""

@@ -106,7 +106,7 @@ def main():
     dist.barrier()
     if rank == 0:
         extra = ""
-        if EMU:   # message counts of the emulated NCCL (lets the caller see that an opt-in schedule really ran)
+        if EMU:   # message counts of the emulated NCCL (lets the caller see which schedule really ran)
             import ctypes
             L = mgb200.capi.lib()
             L.cuda_emu_nccl_sends.restype = L.cuda_emu_nccl_allgathers.restype = ctypes.c_longlong
