@@ -769,7 +769,6 @@ double Ctx::read_norm(const Level& lv)
 // front of the node, because the host-side buffer parities after the first cycle may differ from those it started from;
 // from the second cycle on they must be a fixed point (checked at capture time, else the host loop runs).
 // ---------------------------------------------------------------------------------
-#ifndef MGB_EMU
 struct SolveCtl {
     double r0, rtol;
     int k, max_cycles;
@@ -902,9 +901,6 @@ bool Ctx::solve_device_loop(double rtol, int max_cycles, int nu1, int nu2, int g
     history_last = hist[tail.k];
     return true;
 }
-#else
-bool Ctx::solve_device_loop(double, int, int, int, int, double, int*, double*) { return false; }
-#endif
 
 // Tolerance-controlled loop (the reference runs a fixed count, P:635).  The norm after each cycle comes out
 // of the cycle's own last kernel on the finest level when the fused POST applies (k_stream_norm: no extra pass over the

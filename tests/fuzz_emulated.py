@@ -33,6 +33,8 @@ def main():
         nu1, nu2 = int(rng.integers(0, 5)), int(rng.integers(0, 5))
         gamma = int(rng.integers(1, 4))
         flags = dict(graph=bool(rng.integers(0, 2)), fused=bool(rng.integers(0, 2)), coarse_tail=bool(rng.integers(0, 2)))
+        exact = bool(rng.integers(0, 4) == 0)          # MG_COARSE_EXACT: direct solve on the coarsest level (M:63-72)
+        flags["coarse_solver"] = "exact" if exact else "sweeps"
         env = {k: str(int(rng.integers(0, 2))) for k in ("MGB200_ZERO_GUESS", "MGB200_CHAIN")}
         if os.environ.get("FUZZ_DEFAULT_ONLY") == "1":
             env = {k: "1" for k in env}   # the library defaults
@@ -42,7 +44,8 @@ def main():
         m = (1 << level) - 1
         x = rng.uniform(-1, 1, m * m).astype(dtype)
         b = (1e-3 * rng.uniform(-1, 1, m * m)).astype(dtype)
-        p = oracle.Params(coarsest_level=coarsest, nu1=nu1, nu2=nu2, gamma=gamma, smoother=1 if smoother == "rbgs" else 0, nthreads=1)
+        p = oracle.Params(coarsest_level=coarsest, nu1=nu1, nu2=nu2, gamma=gamma, smoother=1 if smoother == "rbgs" else 0, nthreads=1,
+                          coarse_exact=int(exact))
         try:
             with mgb200.Multigrid(level, coarsest_level=coarsest, dtype=dtype, smoother=smoother, **flags) as mg:
                 mg.set_u(level, x)
@@ -72,12 +75,23 @@ def main():
                 mg.smooth(level, 1 + nu1)
                 want = o.jacobirelaxation(want, b, 1 + nu1) if smoother == "jacobi" else o.rbgs(want, b, 1 + nu1)
                 mg.cycle(level, max(nu1, 1), nu2, gamma)
-                p2 = oracle.Params(coarsest_level=coarsest, nu1=max(nu1, 1), nu2=nu2, gamma=gamma, smoother=p.smoother, nthreads=1)
+                p2 = oracle.Params(coarsest_level=coarsest, nu1=max(nu1, 1), nu2=nu2, gamma=gamma, smoother=p.smoother, nthreads=1,
+                                   coarse_exact=int(exact))
                 want = o.vcyclemultigrid(want, b, p2)
                 if not np.array_equal(mg.get_u(level), want):
                     raise AssertionError("cycle after operator calls differs")
+                if rng.integers(0, 2):      # tolerance loop (norm folded into the cycle's last kernel where it applies)
+                    ps = oracle.Params(coarsest_level=coarsest, nu1=max(nu1, 1), nu2=max(nu2, 1), gamma=gamma, smoother=p.smoother,
+                                       nthreads=1, coarse_exact=int(exact))
+                    mc = int(rng.integers(1, 5))
+                    k, rel, hist = mg.solve(1e-6, mc, ps.nu1, ps.nu2, gamma)
+                    us, ko, ho = o.solve(want, b, 1e-6, mc, ps)
+                    if k != ko or not np.allclose(hist, ho, rtol=1e-9, atol=0) or not np.array_equal(mg.get_u(level), us):
+                        raise AssertionError(f"solve differs: {k} vs {ko} cycles")
+                    want = us
                 if rng.integers(0, 2):
-                    pf = oracle.Params(coarsest_level=coarsest, nu1=max(nu1, 1), nu2=max(nu2, 1), smoother=p.smoother, nthreads=1)
+                    pf = oracle.Params(coarsest_level=coarsest, nu1=max(nu1, 1), nu2=max(nu2, 1), smoother=p.smoother, nthreads=1,
+                                       coarse_exact=int(exact))
                     cyc = 1 + int(rng.integers(0, 2))
                     if not np.array_equal(mg.fullmultigrid(b, cyc, pf.nu1, pf.nu2), o.fullmultigrid(b, cyc, pf)):
                         raise AssertionError("fullmultigrid differs")

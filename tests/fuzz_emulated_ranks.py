@@ -49,7 +49,7 @@ def main():
         flags = dict(graph=bool(rng.integers(0, 2)), fused=bool(rng.integers(0, 4) > 0), coarse_tail=bool(rng.integers(0, 2)))
         env = {k: str(int(rng.integers(0, 2))) for k in KNOBS}
         if os.environ.get("FUZZ_DEFAULT_ONLY") == "1":      # the default configuration only (what the GPU suite runs)
-            env = {k: "0" for k in KNOBS}
+            env = {k: "1" for k in KNOBS}   # the library defaults
         os.environ.update(env)
         cfg = dict(level=level, aggl=aggl, dtype=np.dtype(dtype).name, smoother=smoother, nu1=nu1, nu2=nu2, gamma=gamma, **flags, **env)
         m = (1 << level) - 1
@@ -57,7 +57,7 @@ def main():
         b = (1e-3 * rng.uniform(-1, 1, m * m)).astype(dtype)
         sid = 1 if smoother == "rbgs" else 0
         p = oracle.Params(nu1=nu1, nu2=nu2, gamma=gamma, smoother=sid, nthreads=1)
-        ops = [int(v) for v in rng.integers(0, 6, size=int(rng.integers(2, 6)))]
+        ops = [int(v) for v in rng.integers(0, 7, size=int(rng.integers(2, 6)))]
         cnts = [int(v) for v in rng.integers(2, 4, size=len(ops))]
         try:
             mg = mgdist.create(level, dtype=dtype, smoother=smoother, agglomerate_level=aggl, **flags)
@@ -82,6 +82,12 @@ def main():
                         raise AssertionError("residual differs")
                     if abs(nrm - o.norm2(r)) > 1e-5 * max(o.norm2(r), 1e-30):
                         raise AssertionError("norm differs")
+                elif op == 6:                    # tolerance loop: the norm comes out of the cycle's last kernel where that applies
+                    ps = oracle.Params(nu1=max(nu1, 1), nu2=max(nu2, 1), gamma=gamma, smoother=sid, nthreads=1)
+                    k, rel, hist = mg.solve(1e-6, cnt, ps.nu1, ps.nu2, gamma)
+                    want, ko, ho = o.solve(want, b, 1e-6, cnt, ps)
+                    if k != ko or not np.allclose(hist, ho, rtol=1e-9, atol=0):
+                        raise AssertionError(f"solve differs: {k} vs {ko} cycles, {hist} vs {ho}")
                 elif op == 4:
                     mg.set_u(level, want)        # host round trip: halos become valid again
                 else:

@@ -189,6 +189,36 @@ cudaError_t cudaGraphDestroy(cudaGraph_t g);
 cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e);
 cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t s);
 
+// ---- conditional graph nodes (CUDA 12.4): enough for a WHILE node whose body is populated by capture-to-graph ----
+struct emuCond { unsigned value = 0, dflt = 0; bool assign_default = false; };
+typedef emuCond* cudaGraphConditionalHandle;
+typedef void* cudaGraphNode_t;
+struct cudaGraphEdgeData { int unused; };
+enum cudaStreamCaptureStatus { cudaStreamCaptureStatusNone = 0, cudaStreamCaptureStatusActive = 1, cudaStreamCaptureStatusInvalidated = 2 };
+enum cudaGraphNodeType { cudaGraphNodeTypeKernel = 0, cudaGraphNodeTypeConditional = 13 };
+enum cudaGraphConditionalNodeType { cudaGraphCondTypeIf = 0, cudaGraphCondTypeWhile = 1 };
+enum { cudaGraphCondAssignDefault = 1 };
+enum { cudaStreamAddCaptureDependencies = 0, cudaStreamSetCaptureDependencies = 1 };
+struct cudaConditionalNodeParams {
+    cudaGraphConditionalHandle handle;
+    cudaGraphConditionalNodeType type;
+    unsigned size;
+    cudaGraph_t* phGraph_out;
+};
+struct cudaGraphNodeParams {
+    cudaGraphNodeType type;
+    cudaConditionalNodeParams conditional;
+};
+cudaError_t cudaGraphConditionalHandleCreate(cudaGraphConditionalHandle* h, cudaGraph_t g, unsigned defaultLaunchValue = 0, unsigned flags = 0);
+cudaError_t cudaStreamGetCaptureInfo(cudaStream_t s, cudaStreamCaptureStatus* status, unsigned long long* id = nullptr,
+                                     cudaGraph_t* graph = nullptr, const cudaGraphNode_t** deps = nullptr, size_t* ndeps = nullptr);
+cudaError_t cudaStreamIsCapturing(cudaStream_t s, cudaStreamCaptureStatus* status);
+cudaError_t cudaGraphAddNode(cudaGraphNode_t* node, cudaGraph_t g, const cudaGraphNode_t* deps, size_t ndeps, cudaGraphNodeParams* p);
+cudaError_t cudaStreamUpdateCaptureDependencies(cudaStream_t s, cudaGraphNode_t* deps, size_t ndeps, unsigned flags);
+cudaError_t cudaStreamBeginCaptureToGraph(cudaStream_t s, cudaGraph_t g, const cudaGraphNode_t* deps, const cudaGraphEdgeData* data,
+                                          size_t ndeps, cudaStreamCaptureMode m);
+inline void cudaGraphSetConditional(cudaGraphConditionalHandle h, unsigned value) { h->value = value; }   // "device" side
+
 template <typename F>
 inline cudaError_t cudaFuncSetAttribute(F* fn, cudaFuncAttribute a, int v)
 {

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -311,10 +312,14 @@ static void run_kernel(dim3 grid, dim3 block, size_t smem, unsigned cluster, con
 struct emuGraph {
     std::vector<std::function<void()>> ops;
     int forked = 0;    // streams pulled into the capture and not joined back yet
+    std::vector<emuCond*> conds;                        // conditional handles created for this graph (reset at launch)
+    std::vector<std::shared_ptr<emuGraph>> bodies;      // bodies of conditional nodes (shared with instantiated copies)
+    std::vector<cudaGraph_t> body_ptrs;                 // phGraph_out storage
 };
 struct emuStream {
     emuGraph* capture = nullptr;
     bool joined_capture = false;   // this stream was pulled into another stream's capture by cudaStreamWaitEvent (fork)
+    bool capture_to_graph = false; // cudaStreamBeginCaptureToGraph: the graph belongs to somebody else
 };
 struct emuEvent {
     std::chrono::steady_clock::time_point t;
@@ -508,11 +513,12 @@ cudaError_t cudaStreamBeginCapture(cudaStream_t s, cudaStreamCaptureMode)
 cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t* g)
 {
     if (!s || !s->capture || s->joined_capture || s->capture->forked != 0) {   // unjoined work in another stream
-        *g = nullptr;
+        if (g) *g = nullptr;
         return cudaErrorInvalidValue;
     }
-    *g = s->capture;
+    if (g) *g = s->capture;
     s->capture = nullptr;
+    s->capture_to_graph = false;
     return cudaSuccess;
 }
 cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long)
@@ -525,7 +531,70 @@ cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { delete e; return cudaSucce
 cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t s)
 {
     if (s && s->capture) return cudaErrorStreamCaptureUnsupported;
+    for (emuCond* c : e->conds)
+        if (c->assign_default) c->value = c->dflt;
     for (auto& op : e->ops) op();
+    return cudaSuccess;
+}
+
+// ---- conditional WHILE nodes ----
+cudaError_t cudaGraphConditionalHandleCreate(cudaGraphConditionalHandle* h, cudaGraph_t g, unsigned dflt, unsigned flags)
+{
+    if (!h || !g) return cudaErrorInvalidValue;
+    emuCond* c = new emuCond();          // lives as long as the process: instantiated copies keep using it
+    c->dflt = dflt;
+    c->value = dflt;
+    c->assign_default = (flags & cudaGraphCondAssignDefault) != 0;
+    g->conds.push_back(c);
+    *h = c;
+    return cudaSuccess;
+}
+cudaError_t cudaStreamGetCaptureInfo(cudaStream_t s, cudaStreamCaptureStatus* status, unsigned long long* id, cudaGraph_t* graph,
+                                     const cudaGraphNode_t** deps, size_t* ndeps)
+{
+    if (!s || !status) return cudaErrorInvalidValue;
+    *status = s->capture ? cudaStreamCaptureStatusActive : cudaStreamCaptureStatusNone;
+    if (id) *id = 1;
+    if (graph) *graph = s->capture;
+    if (deps) *deps = nullptr;
+    if (ndeps) *ndeps = 0;
+    return cudaSuccess;
+}
+cudaError_t cudaStreamIsCapturing(cudaStream_t s, cudaStreamCaptureStatus* status)
+{
+    if (!status) return cudaErrorInvalidValue;
+    *status = (s && s->capture) ? cudaStreamCaptureStatusActive : cudaStreamCaptureStatusNone;
+    return cudaSuccess;
+}
+cudaError_t cudaGraphAddNode(cudaGraphNode_t* node, cudaGraph_t g, const cudaGraphNode_t*, size_t, cudaGraphNodeParams* p)
+{
+    if (!g || !p || p->type != cudaGraphNodeTypeConditional || p->conditional.type != cudaGraphCondTypeWhile || p->conditional.size != 1)
+        return cudaErrorInvalidValue;
+    auto body = std::make_shared<emuGraph>();
+    g->bodies.push_back(body);
+    g->body_ptrs.push_back(body.get());
+    emuCond* c = p->conditional.handle;
+    g->ops.push_back([body, c]() {               // in issue order: everything captured before the node has run
+        int guard = 0;
+        while (c->value) {
+            for (auto& op : body->ops) op();
+            if (++guard > 1000000) break;         // a body that never clears its condition
+        }
+    });
+    p->conditional.phGraph_out = &g->body_ptrs.back();
+    if (node) *node = (cudaGraphNode_t)body.get();
+    return cudaSuccess;
+}
+cudaError_t cudaStreamUpdateCaptureDependencies(cudaStream_t s, cudaGraphNode_t*, size_t, unsigned)
+{
+    return (s && s->capture) ? cudaSuccess : cudaErrorInvalidValue;   // closures replay in issue order anyway
+}
+cudaError_t cudaStreamBeginCaptureToGraph(cudaStream_t s, cudaGraph_t g, const cudaGraphNode_t*, const cudaGraphEdgeData*, size_t,
+                                          cudaStreamCaptureMode)
+{
+    if (!s || s->capture || !g) return cudaErrorInvalidValue;
+    s->capture = g;
+    s->capture_to_graph = true;
     return cudaSuccess;
 }
 

@@ -374,7 +374,7 @@ def test_solve_as_one_device_side_loop(mgb, orc, knob, level, smoother, gamma):
             if max_cycles == 60:
                 assert k == k0 and np.allclose(hist, h0, rtol=1e-12, atol=0)
                 assert_bitwise(mg.get_u(level), u0, "device loop vs host loop")
-            if level >= 8 and not conftest.EMULATED:     # (the CPU emulation build has no conditional graph nodes: host loop)
+            if level >= 8:
                 assert mg.info(mgb.capi.MG_INFO_GRAPH_LAUNCHES) - g0 == 1, "the whole solve must be one graph launch"
         mg.cycle(level, 2, 2, gamma)                     # ordinary calls still work on the state the loop left
         assert_bitwise(mg.get_u(level), orc.vcyclemultigrid(u, b, p), "cycle after a device-loop solve")
