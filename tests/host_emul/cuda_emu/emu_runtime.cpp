@@ -655,6 +655,12 @@ static int put(const std::string& path, const void* buf, size_t bytes)
 {
     const std::string tmp = path + ".tmp";
     FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f) {
+        // a rank that finished early removes the (momentarily empty) directory in CommDestroy while slower ranks still
+        // exchange messages among themselves: re-create it
+        mkdir(path.substr(0, path.rfind('/')).c_str(), 0700);
+        f = std::fopen(tmp.c_str(), "wb");
+    }
     if (!f) return 2;
     const size_t w = bytes ? std::fwrite(buf, 1, bytes, f) : 0;
     std::fclose(f);
