@@ -442,6 +442,23 @@ def test_errors_are_loud(mgb):
             mg.set_u(5, np.zeros(10))
     with pytest.raises(mgb.capi.MgError):
         mgb.Multigrid(3, coarsest_level=4)
+    with pytest.raises(mgb.capi.MgError):                       # the sine-transform table of the exact solve is n x n: n <= 511
+        mgb.Multigrid(11, coarsest_level=10, coarse_solver="exact")
+    with make(mgb, 4) as mg:
+        import ctypes
+        out = ctypes.c_uint64(0)
+        L = mgb.capi.lib()
+        assert L.mg_checksum(mg._ctx, 4, 7, ctypes.byref(out)) == mgb.capi.MG_ERR_ARG      # which not in {u, f, r}
+        assert L.mg_checksum(mg._ctx, 4, 0, None) == mgb.capi.MG_ERR_ARG
+        assert L.mg_checksum(mg._ctx, 9, 0, ctypes.byref(out)) == mgb.capi.MG_ERR_ARG      # level outside the hierarchy
+        assert b"level" in L.mg_last_error(mg._ctx)
+        k, rel, hist = mg.solve(1e-8, 0)                        # max_cycles = 0: no cycle, history = the initial norm only
+        assert k == 0 and len(hist) == 1
+    # a failed mg_create leaves nothing behind: the next context on the same device works
+    with make(mgb, 5) as mg:
+        mg.force_constant(4.0)
+        mg.zero_u(5)
+        assert mg.solve(1e-8, 30)[0] > 0
 
 
 def test_cpp_driver_example_runs_like_the_reference_main(mgb, tmp_path):
