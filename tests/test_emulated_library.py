@@ -49,8 +49,7 @@ def torchrun_cmd(world, script, *args):
 WORKER = os.path.join(ROOT, "tests", "mgpu_worker.py")
 BENCH_WORKER = os.path.join(ROOT, "tests", "host_emul", "bench_emu_worker.py")
 KNOBS = {"default": {}, "lazy_exchanges_eager": {"MGB200_COMM_AVOID": "0", "MGB200_GRAPH_DIST": "0"},
-         "no_chain_no_zero_guess": {"MGB200_CHAIN": "0", "MGB200_ZERO_GUESS": "0"}, "lazy_exchanges_graph": {"MGB200_COMM_AVOID": "0"},
-         "comm_avoid_eager": {"MGB200_GRAPH_DIST": "0"}}
+         "no_chain_no_zero_guess": {"MGB200_CHAIN": "0", "MGB200_ZERO_GUESS": "0"}, "lazy_exchanges_graph": {"MGB200_COMM_AVOID": "0"}}
 BENCH = {"1rank": (1, []), "2ranks_slab_host_buffers": (2, ["--aggl", "5", "--level", "8"]), "rbgs_wcycle": (1, ["--smoother", "rbgs", "--gamma", "2"])}
 
 
@@ -73,6 +72,9 @@ class Jobs:
         }
         for name, knobs in KNOBS.items():
             jobs["slabs:" + name] = (torchrun_cmd(2, WORKER), {"MGB200_WORKER_QUICK": "1", "OMP_NUM_THREADS": "1", **knobs})
+        # four ranks: the smallest world with INTERIOR ranks (two neighbours each); round 2 had a bug only they could show
+        for name in ("default", "lazy_exchanges_eager"):
+            jobs["slabs4:" + name] = (torchrun_cmd(4, WORKER), {"MGB200_WORKER_QUICK": "1", "OMP_NUM_THREADS": "1", **KNOBS[name]})
         for name, (world, extra) in BENCH.items():
             cmd = [sys.executable, BENCH_WORKER, "--level", "6", *extra] if world == 1 else torchrun_cmd(world, BENCH_WORKER, *extra)
             jobs["bench:" + name] = (cmd, {"OMP_NUM_THREADS": "1"})
@@ -134,6 +136,13 @@ def test_two_rank_row_slabs_under_emulation(jobs, name):
         sends = int(out.split("sends=")[1].split()[0])
         default_sends = int(jobs.result("slabs:default").split("sends=")[1].split()[0])
         assert default_sends < 0.75 * sends, (sends, default_sends)
+
+
+@pytest.mark.parametrize("name", ["default", "lazy_exchanges_eager"])
+def test_four_rank_row_slabs_under_emulation(jobs, name):
+    """The same worker on 4 CPU ranks: ranks 1 and 2 are interior ranks with a neighbour on either side."""
+    out = jobs.result("slabs4:" + name)
+    assert "MGPU OK world=4" in out, out[-3000:]
 
 
 BENCH_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
