@@ -641,6 +641,31 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         strong = res[0]
 
+    # ---- N > 1: where the distributed cycle goes.  Device time per phase of the communication-avoiding plan from eagerly
+    #      launched cycles with CUDA events around every op (mg_time_phases); per phase: max and mean over the ranks.
+    #      COLLECTIVE: every rank runs it (the cycles exchange halos), rank 0 reports ----
+    phases = None
+    if world > 1 and not args.no_phases:
+        try:
+            ph = mg.time_phases(level, nu1, nu2, gamma, 5)
+        except Exception as ex:  # noqa: BLE001 - informational leg only
+            ph = {"error": str(ex)}
+        allp = [None] * world
+        dist.all_gather_object(allp, ph)
+        if all(p and "error" not in p for p in allp):
+            names = [k for k in allp[0] if k != "ops_per_cycle"]
+            tot = {k: [sum(p.get(k, {}).values()) for p in allp] for k in names}
+            phases = {"how": "5 eager (un-captured) cycles, CUDA events around every op of the communication-avoiding plan; "
+                             "includes the launch gaps of eager launches",
+                      "per_phase_max_over_ranks": {k: max(v) for k, v in tot.items()},
+                      "per_phase_mean_over_ranks": {k: sum(v) / world for k, v in tot.items()},
+                      "sum_of_phases_max_rank": max(sum(tot[k][r] for k in names) for r in range(world)),
+                      "rank0_by_level": {k: allp[0][k] for k in names},
+                      "captured_cycle_ms": isolated_ms}
+        else:
+            errs = [p.get("error") for p in allp if p and "error" in p]
+            phases = {"unavailable": errs[0] if errs else "this schedule does not run the communication-avoiding plan"}
+
     # ---- N > 1: the weighted-Jacobi cycle on the same grid (round 1's scaling workload), timing only ----
     extra = None
     if world > 1 and smoother != "jacobi" and not args.no_extra:
@@ -693,6 +718,8 @@ def run_ours(args, rank, world, local_rank):
             "finest_points_per_s": n * n / (ms_step * 1e-3),
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
     line["solve"] = solve_info
+    if phases is not None:
+        line["phases_ms"] = phases
     if strong is not None:
         line["strong_scaling"] = strong
         line["n1_same_workload"] = ({"ms_per_step": strong["n1_ms_per_step"], "value": strong["n1_value"], "unit": UNIT,
@@ -798,6 +825,7 @@ def main():
     ap.add_argument("--aggl", type=int, default=0, help="agglomeration level for N>1 (0 = library default)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (tuning runs)")
     ap.add_argument("--no-n1", action="store_true", help="N>1: skip the single-GPU run of the same workload on rank 0 (strong_scaling, mgpu_parity)")
+    ap.add_argument("--no-phases", action="store_true", help="N>1: skip the per-phase timing of the distributed cycle")
     ap.add_argument("--no-extra", action="store_true", help="N>1: skip the extra weighted-Jacobi timing on the same grid")
     ap.add_argument("--micro", action="store_true",
                     help="BASELINE configs[4]: smoother/residual micro-benchmark (default 32769^2; use --dtype f32)")

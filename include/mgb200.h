@@ -142,6 +142,12 @@ int mg_plan_vcycle(int top_level, int agglomerate_level, int world, int rank, in
 int mg_time_op(mg_ctx* ctx, int op, int level, int reps, float* ms_out);
 /* `reps` back-to-back mg_cycle calls bracketed by CUDA events on the context's stream */
 int mg_time_cycle(mg_ctx* ctx, int level, int nu1, int nu2, int gamma, int reps, float* ms_out);
+/* Row slabs (world > 1), communication-avoiding schedule: device milliseconds per cycle of every phase of the plan, from
+ * `reps` eagerly launched cycles with a pair of CUDA events around each op (launch gaps of eager launches included).
+ * out_ms_5x32[kind * 32 + level], kinds as in mg_plan_vcycle: 0 halo exchange, 1 PRE, 2 POST, 3 all-gather of the first
+ * replicated level's right-hand side, 4 the replicated coarse cycle.  *ops_per_cycle = 0 when this context does not run
+ * the plan (one GPU, lazy schedule). */
+int mg_time_phases(mg_ctx* ctx, int level, int nu1, int nu2, int gamma, int reps, double* out_ms_5x32, int* ops_per_cycle);
 enum { MG_OP_SMOOTH1 = 0, MG_OP_RESIDUAL = 1, MG_OP_RESTRICT = 2, MG_OP_PROLONG = 3,
        MG_OP_PRE_FUSED = 4, MG_OP_POST_FUSED = 5, MG_OP_RESIDUAL_NORM = 6, MG_OP_SMOOTH2 = 7,
        MG_OP_SMOOTH3 = 8, MG_OP_SMOOTH4 = 9, /* k sweeps temporally blocked in ONE launch (k = 4: Jacobi only) */

@@ -111,6 +111,7 @@ def lib() -> ctypes.CDLL:
         "mg_plan_vcycle": (ci, [ci, ci, ci, ci, ci, ci, ci, ci, ctypes.POINTER(ci), ci, ctypes.POINTER(ci)]),
         "mg_time_op": (ci, [vp, ci, ci, ci, ctypes.POINTER(ctypes.c_float)]),
         "mg_time_cycle": (ci, [vp, ci, ci, ci, ci, ci, ctypes.POINTER(ctypes.c_float)]),
+        "mg_time_phases": (ci, [vp, ci, ci, ci, ci, ci, ctypes.POINTER(cd), ctypes.POINTER(ci)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -283,6 +283,14 @@ int mg_time_op(mg_ctx* c, int op, int level, int reps, float* ms_out)
     });
 }
 
+int mg_time_phases(mg_ctx* c, int level, int nu1, int nu2, int gamma, int reps, double* out_ms_5x32, int* ops_per_cycle)
+{
+    return guarded(c, [&](Ctx& x) {
+        const int n = x.time_phases(level, nu1, nu2, gamma, reps, out_ms_5x32);
+        if (ops_per_cycle) *ops_per_cycle = n;
+    });
+}
+
 int mg_time_cycle(mg_ctx* c, int level, int nu1, int nu2, int gamma, int reps, float* ms_out)
 {
     return guarded(c, [&](Ctx& x) {

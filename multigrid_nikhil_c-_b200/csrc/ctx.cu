@@ -691,7 +691,7 @@ void Ctx::cycles(int level, int nu1, int nu2, int gamma, int count)
         for (int i = 0; i < count; ++i) cycles(level, nu1, nu2, gamma, 1);
         return;
     }
-    if (!(cfg.flags & MG_GRAPH) || capturing || (cfg.world > 1 && !graph_dist)) {
+    if (!(cfg.flags & MG_GRAPH) || capturing || force_eager || (cfg.world > 1 && !graph_dist)) {
         cycle_rec_visits(level, nu1, nu2, gamma, count);
         return;
     }
@@ -934,6 +934,36 @@ int Ctx::solve(double rtol, int max_cycles, int nu1, int nu2, int gamma, double*
     }
     if (relres) *relres = (r0 > 0.0) ? rk / r0 : 0.0;
     return k;
+}
+
+int Ctx::time_phases(int level, int nu1, int nu2, int gamma, int reps, double* out)
+{
+    MG_REQUIRE(reps >= 1 && out != nullptr, "reps >= 1 and an output array of 5 x 32 doubles required");
+    L(level);
+    for (int i = 0; i < 5 * 32; ++i) out[i] = 0.0;
+    struct Restore {
+        Ctx& c;
+        ~Restore()
+        {
+            c.force_eager = c.phase_on = false;
+            for (PhaseRec& r : c.phase_log) {
+                if (r.e0) cudaEventDestroy(r.e0);
+                if (r.e1) cudaEventDestroy(r.e1);
+            }
+            c.phase_log.clear();
+        }
+    } restore{*this};
+    force_eager = true;
+    cycles(level, nu1, nu2, gamma, 1);      // warm (tuner, first exchange of the static right-hand side), not logged
+    phase_on = true;
+    for (int i = 0; i < reps; ++i) cycles(level, nu1, nu2, gamma, 1);
+    MG_CK(cudaStreamSynchronize(stream));
+    for (const PhaseRec& r : phase_log) {
+        float ms = 0.f;
+        MG_CK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        if (r.kind >= 0 && r.kind < 5 && r.level >= 0 && r.level < 32) out[r.kind * 32 + r.level] += (double)ms / reps;
+    }
+    return (int)(phase_log.size() / (size_t)reps);
 }
 
 float Ctx::time_op(int op, int level, int reps)

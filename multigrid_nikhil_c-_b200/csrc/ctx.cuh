@@ -121,6 +121,12 @@ struct Stager {
     bool ready = false;
 };
 
+// one timed op of the communication-avoiding plan (mg_time_phases)
+struct PhaseRec {
+    int kind = 0, level = 0;           // SchedKind, level
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
 struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
     long long kernels = 0;
@@ -203,6 +209,12 @@ struct Ctx {
     void fmg(int cycles, int nu1, int nu2);
     int solve(double rtol, int max_cycles, int nu1, int nu2, int gamma, double* relres, double* history);
     float time_op(int op, int level, int reps);
+    // per-phase device time of the communication-avoiding cycle (world > 1): `reps` EAGER cycles with a pair of events around
+    // every op of the plan; out[kind * 32 + level] = milliseconds per cycle (kinds: sched.h SchedKind).  Returns the number
+    // of timed ops per cycle (0: this context does not run the plan).
+    int time_phases(int level, int nu1, int nu2, int gamma, int reps, double* out160);
+    bool phase_on = false, force_eager = false;
+    std::vector<PhaseRec> phase_log;
     double read_norm(const Level& lv);
     // the whole tolerance loop as ONE graph launch: a conditional WHILE node whose body is the cycle (device-side decision)
     bool solve_device_loop(double rtol, int max_cycles, int nu1, int nu2, int gamma, double r0, int* k_out, double* history);

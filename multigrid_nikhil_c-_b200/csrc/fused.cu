@@ -614,55 +614,75 @@ static void launch_stream_range(Ctx& ctx, Level& lv, Level* lcv, int ya, int yb)
 }
 
 template <typename T>
-static void comm_avoid_run(Ctx& ctx, const SchedPlan& plan, int nu1, int nu2)
+static void comm_avoid_op(Ctx& ctx, const SchedPlan& plan, const SchedOp& op, int nu1, int nu2)
 {
     const bool rb = ctx.cfg.smoother == MG_SMOOTH_RBGS;
+    Level& lv = ctx.L(op.level);
+    switch (op.kind) {
+        case SCHED_EXCH: {
+            comm_halo_exchange(ctx, lv, op.a == 0 ? lv.u[lv.cur] : lv.f, op.b);
+            if (op.a == 0) lv.hv_u = op.b; else lv.hv_f = op.b;
+            break;
+        }
+        case SCHED_PRE: {
+            Level& lcv = ctx.L(op.level - 1);
+            if (lcv.distributed) comm_zero_halo(ctx, lcv, lcv.u[0]);   // rows of the zero guess the kernel does not reach
+            if (!rb) {
+                if (nu1 == 2) launch_stream_range<T, 2, MODE_PRE, false>(ctx, lv, &lcv, op.a, op.b);
+                else launch_stream_range<T, 1, MODE_PRE, false>(ctx, lv, &lcv, op.a, op.b);
+            } else {
+                if (nu1 == 2) launch_stream_range<T, 4, MODE_PRE, true>(ctx, lv, &lcv, op.a, op.b);
+                else launch_stream_range<T, 2, MODE_PRE, true>(ctx, lv, &lcv, op.a, op.b);
+            }
+            lv.hv_u = plan.e[op.level];
+            lcv.u_zero = false;
+            if (lcv.distributed) {
+                lcv.hv_f = plan.e[op.level] / 2;
+                lcv.hv_u = lcv.halo;
+            }
+            break;
+        }
+        case SCHED_GATHER_F: {
+            comm_allgather_rows(ctx, lv, lv.f);
+            lv.cur = 0;
+            MG_CK(cudaMemsetAsync(lv.alloc[0], 0, lv.bytes, ctx.stream));
+            break;
+        }
+        case SCHED_REPL_CYCLE: ctx.cycle_rec(op.level, nu1, nu2, 1); break;
+        case SCHED_POST: {
+            Level& lcv = ctx.L(op.level - 1);
+            if (!rb) {
+                if (nu2 == 2) launch_stream_range<T, 2, MODE_POST, false>(ctx, lv, &lcv, op.a, op.b);
+                else launch_stream_range<T, 1, MODE_POST, false>(ctx, lv, &lcv, op.a, op.b);
+            } else {
+                if (nu2 == 2) launch_stream_range<T, 4, MODE_POST, true>(ctx, lv, &lcv, op.a, op.b);
+                else launch_stream_range<T, 2, MODE_POST, true>(ctx, lv, &lcv, op.a, op.b);
+            }
+            lv.hv_u = plan.x[op.level];
+            break;
+        }
+    }
+}
+
+template <typename T>
+static void comm_avoid_run(Ctx& ctx, const SchedPlan& plan, int nu1, int nu2)
+{
     ctx.materialize_u(ctx.L(plan.ops.front().level));
     for (const SchedOp& op : plan.ops) {
-        Level& lv = ctx.L(op.level);
-        switch (op.kind) {
-            case SCHED_EXCH: {
-                comm_halo_exchange(ctx, lv, op.a == 0 ? lv.u[lv.cur] : lv.f, op.b);
-                if (op.a == 0) lv.hv_u = op.b; else lv.hv_f = op.b;
-                break;
-            }
-            case SCHED_PRE: {
-                Level& lcv = ctx.L(op.level - 1);
-                if (lcv.distributed) comm_zero_halo(ctx, lcv, lcv.u[0]);   // rows of the zero guess the kernel does not reach
-                if (!rb) {
-                    if (nu1 == 2) launch_stream_range<T, 2, MODE_PRE, false>(ctx, lv, &lcv, op.a, op.b);
-                    else launch_stream_range<T, 1, MODE_PRE, false>(ctx, lv, &lcv, op.a, op.b);
-                } else {
-                    if (nu1 == 2) launch_stream_range<T, 4, MODE_PRE, true>(ctx, lv, &lcv, op.a, op.b);
-                    else launch_stream_range<T, 2, MODE_PRE, true>(ctx, lv, &lcv, op.a, op.b);
-                }
-                lv.hv_u = plan.e[op.level];
-                lcv.u_zero = false;
-                if (lcv.distributed) {
-                    lcv.hv_f = plan.e[op.level] / 2;
-                    lcv.hv_u = lcv.halo;
-                }
-                break;
-            }
-            case SCHED_GATHER_F: {
-                comm_allgather_rows(ctx, lv, lv.f);
-                lv.cur = 0;
-                MG_CK(cudaMemsetAsync(lv.alloc[0], 0, lv.bytes, ctx.stream));
-                break;
-            }
-            case SCHED_REPL_CYCLE: ctx.cycle_rec(op.level, nu1, nu2, 1); break;
-            case SCHED_POST: {
-                Level& lcv = ctx.L(op.level - 1);
-                if (!rb) {
-                    if (nu2 == 2) launch_stream_range<T, 2, MODE_POST, false>(ctx, lv, &lcv, op.a, op.b);
-                    else launch_stream_range<T, 1, MODE_POST, false>(ctx, lv, &lcv, op.a, op.b);
-                } else {
-                    if (nu2 == 2) launch_stream_range<T, 4, MODE_POST, true>(ctx, lv, &lcv, op.a, op.b);
-                    else launch_stream_range<T, 2, MODE_POST, true>(ctx, lv, &lcv, op.a, op.b);
-                }
-                lv.hv_u = plan.x[op.level];
-                break;
-            }
+        // mg_time_phases: a pair of events around every op of the plan (eager launches only; see Ctx::time_phases)
+        const bool timed = ctx.phase_on && !ctx.capturing;
+        PhaseRec rec;
+        if (timed) {
+            rec.kind = op.kind;
+            rec.level = op.level;
+            MG_CK(cudaEventCreate(&rec.e0));
+            MG_CK(cudaEventCreate(&rec.e1));
+            MG_CK(cudaEventRecord(rec.e0, ctx.stream));
+        }
+        comm_avoid_op<T>(ctx, plan, op, nu1, nu2);
+        if (timed) {
+            MG_CK(cudaEventRecord(rec.e1, ctx.stream));
+            ctx.phase_log.push_back(rec);
         }
     }
 }

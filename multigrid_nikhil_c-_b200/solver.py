@@ -247,6 +247,22 @@ class Multigrid:
         self._ck(self._lib.mg_time_cycle(self._ctx, level, nu1, nu2, gamma, reps, ctypes.byref(ms)))
         return float(ms.value)
 
+    def time_phases(self, level: int, nu1: int, nu2: int, gamma: int, reps: int) -> dict:
+        """Row slabs, communication-avoiding schedule: device ms per cycle of every phase of the plan (mg_time_phases).
+        Returns {} when this context does not run the plan, else {phase: {level: ms}} + {"ops_per_cycle": n}."""
+        out = (ctypes.c_double * 160)()
+        n = ctypes.c_int(0)
+        self._ck(self._lib.mg_time_phases(self._ctx, level, nu1, nu2, gamma, reps, out, ctypes.byref(n)))
+        if n.value == 0:
+            return {}
+        names = ["halo_exchange", "pre", "post", "allgather_rhs", "replicated_coarse_cycle"]
+        res = {"ops_per_cycle": int(n.value)}
+        for k, name in enumerate(names):
+            d = {str(l): out[k * 32 + l] for l in range(32) if out[k * 32 + l] > 0.0}
+            if d:
+                res[name] = d
+        return res
+
     # -- the reference's function surface (host vectors in, host vectors out) --
     def globalforcefunction(self, f: float = 4.0) -> np.ndarray:
         """P:283-335: the finest-level load vector b = f*h^2."""

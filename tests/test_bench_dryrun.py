@@ -59,6 +59,9 @@ class StubMG:
     def cycle(self, level=None, nu1=2, nu2=2, gamma=1):
         self._launches += 13
 
+    def time_phases(self, level, nu1, nu2, gamma, reps):
+        return {"ops_per_cycle": 3, "halo_exchange": {str(level): 0.03}, "pre": {str(level): 0.2}, "post": {str(level): 0.2}} if self.world > 1 else {}
+
     def cycles(self, count, level=None, nu1=2, nu2=2, gamma=1):
         self._launches += 13 * count
 
@@ -98,7 +101,7 @@ class StubMG:
 def _args(**kw):
     d = dict(gpus=1, steps=3, warmup=1, impl="ours", level=6, dtype="f64", smoother="jacobi", nu1=2, nu2=2, gamma=1,
              no_graph=False, no_fused=False, no_tail=False, no_cpu=True, aggl=0, no_e2e=False, full_host_vectors=False, no_n1=False,
-             no_extra=False, micro=False)
+             no_extra=False, no_phases=False, micro=False)
     d.update(kw)
     return argparse.Namespace(**d)
 
@@ -122,7 +125,8 @@ def test_bench_control_flow_and_json_contract(monkeypatch, world):
         import torch.distributed as dist
         monkeypatch.setattr(dist, "init_process_group", lambda *a, **k: None)
         monkeypatch.setattr(dist, "broadcast_object_list", lambda *a, **k: None)
-        monkeypatch.setattr(dist, "all_gather_object", lambda lst, obj: lst.__setitem__(slice(None), [obj] + [0] * (len(lst) - 1)))
+        monkeypatch.setattr(dist, "all_gather_object", lambda lst, obj: lst.__setitem__(
+            slice(None), [obj] * len(lst) if isinstance(obj, dict) else [obj] + [0] * (len(lst) - 1)))
         monkeypatch.setattr(dist, "barrier", lambda *a, **k: None)
         monkeypatch.setattr(dist, "all_reduce", lambda *a, **k: None)
         monkeypatch.setattr(dist, "destroy_process_group", lambda *a, **k: None)
@@ -142,6 +146,7 @@ def test_bench_control_flow_and_json_contract(monkeypatch, world):
     if world > 1:
         ss = d["strong_scaling"]
         assert set(["n1_ms_per_step", "speedup", "efficiency", "mgpu_parity", "checksum_1gpu", "checksum_ngpu"]) <= set(ss)
+        assert d["phases_ms"]["per_phase_max_over_ranks"]["pre"] == pytest.approx(0.2)
         assert d["config"]["smoother"] == "jacobi"     # explicit --smoother wins; the default at N > 1 is rbgs
         assert bench.default_workload(_args(level=0, smoother=None), 2) == (14, "rbgs")
         assert bench.default_workload(_args(level=0, smoother=None), 1) == (12, "jacobi")
