@@ -111,6 +111,59 @@ class ClockSampler:
                 "samples": len(self.samples), "samples_under_load": len(busy)}
 
 
+class LegGuard:
+    """Keeps the one JSON line safe from a hang in an informational leg of an N > 1 run.
+
+    The core measurement (value, roofline, e2e) is in `line` before any optional leg starts.  Every optional leg of a
+    multi-rank run is collective (tolerance solve, parity run, per-phase timing, the extra Jacobi timing): if one rank
+    stalls inside NCCL, all do, the driver's timeout ends the job and the whole record is lost.  Each leg therefore runs
+    under a deadline; when it passes, rank 0 prints the line as it stands (with `aborted_leg`) and every rank leaves with
+    os._exit(0) -- every rank arms the same deadline at the same barrier.  The hung call holds no GIL (ctypes / torch
+    release it), so the timer thread runs."""
+
+    def __init__(self, rank: int, line: dict, enabled: bool, budget_s: float):
+        self.rank, self.line, self.enabled, self.budget_s = rank, line, enabled, budget_s
+        self._lock = threading.Lock()
+        self._printed = False
+        self._timer = None
+        self._name = None
+
+    def _fire(self):
+        with self._lock:
+            if not self._printed:
+                self._printed = True
+                self.line["aborted_leg"] = {"leg": self._name, "after_s": self.budget_s,
+                                            "note": "informational leg did not finish; the core measurement above is complete"}
+                if self.rank == 0:
+                    print(json.dumps(self.line, default=str), flush=True)
+        os._exit(0)
+
+    def __call__(self, name: str):
+        self._name = name
+        return self
+
+    def __enter__(self):
+        if self.enabled:
+            self._timer = threading.Timer(self.budget_s, self._fire)
+            self._timer.daemon = True
+            self._timer.start()
+        return self
+
+    def __exit__(self, *a):
+        if self._timer is not None:
+            self._timer.cancel()
+            self._timer = None
+        return False
+
+    def print_final(self):
+        with self._lock:
+            if self._printed:
+                return
+            self._printed = True
+            if self.rank == 0:
+                print(json.dumps(self.line), flush=True)
+
+
 def synthetic_rhs(level: int, dtype) -> np.ndarray:
     """SURVEY 8d input (ii): b = h^2 * U(-1,1), numpy default_rng(1234), row-major interior order."""
     n = (1 << level) - 1
@@ -581,32 +634,53 @@ def run_ours(args, rank, world, local_rank):
         except Exception as ex:  # noqa: BLE001 - informational leg only
             e2e["fullmultigrid_call"] = {"error": str(ex)}
 
+    # ---- the line as far as the core measurement goes; the legs below add to it.  At N > 1 every one of them is
+    #      collective, so each runs under a deadline (LegGuard): a stall there costs that leg, not the record ----
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" if dtype == np.float64 else "f32", "data": "synthetic",
+            "config": {"workload": workload_name(level, args.dtype, nu1, nu2, gamma, smoother),
+                       "decomposition": "one GPU" if world == 1 else f"row slabs over {world} GPUs, halo exchange over NVLink (NCCL), coarse levels agglomerated",
+                       "level": level, "smoother": smoother, "rhs": rhs_desc, "updates_per_cycle": upd,
+                       "l2_policy": "inputs larger than L2 (4 arrays x %.0f MB on the finest level)" % (n * n * esize / 1e6),
+                       "regions": regions, "region_stat": "median",
+                       "agglomerate_level": mg.info(capi.MG_INFO_AGGLOMERATE_LEVEL, level) if world > 1 else (args.aggl or None),
+                       "timed_as": f"{K} consecutive cycles per region through mg_time_cycle (mg_cycles: POST of one cycle and PRE of "
+                                   f"the next are one launch on the finest level); isolated_cycle_ms = one mg_cycle at a time",
+                       "scaling_note": ("N=1 measures BASELINE configs[1] (4097^2 Jacobi), N>1 measures configs[2] (16385^2 RB-GS): "
+                                        "same-workload speed-up / efficiency are in strong_scaling, not in value(N)/value(1)"),
+                       "env_knobs": {k: v for k, v in sorted(os.environ.items()) if k.startswith("MGB200_")},
+                       "flags": flags},
+            "isolated_cycle_ms": isolated_ms,
+            "finest_points_per_s": n * n / (ms_step * 1e-3),
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    guard = LegGuard(rank, line, enabled=world > 1, budget_s=args.leg_timeout)
+
     # tolerance-controlled solve on the same right-hand side (the reference runs a fixed number of cycles
     # and prints only the vector length): cycle count, residual history, wall time incl. the per-cycle norm
-    solve_info = None
-    try:
-        if world > 1:
-            mg.force_synthetic(SEED)
-        mg.zero_u(level)
-        mg.solve(1e-8, 2, nu1, nu2, gamma)      # warm (graphs of the solve path)
-        mg.zero_u(level)
-        mg.sync()
-        barrier()
-        t0 = time.perf_counter()
-        k_cyc, relres, hist = mg.solve(1e-8, 40, nu1, nu2, gamma)
-        mg.sync()
-        solve_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-        solve_info = {"rtol": 1e-8, "cycles": k_cyc, "relres": relres, "ms": solve_ms, "ms_per_cycle": solve_ms / max(k_cyc, 1),
-                      "overhead_vs_isolated_cycle": solve_ms / max(k_cyc, 1) / isolated_ms - 1.0,
-                      "residual_history": [float(h) for h in hist],
-                      "factors": [float(hist[i + 1] / hist[i]) for i in range(len(hist) - 1) if hist[i] > 0]}
-    except Exception as ex:  # noqa: BLE001 - informational leg only
-        solve_info = {"error": str(ex)}
+    with guard("solve"):
+        try:
+            if world > 1:
+                mg.force_synthetic(SEED)
+            mg.zero_u(level)
+            mg.solve(1e-8, 2, nu1, nu2, gamma)      # warm (graphs of the solve path)
+            mg.zero_u(level)
+            mg.sync()
+            barrier()
+            t0 = time.perf_counter()
+            k_cyc, relres, hist = mg.solve(1e-8, 40, nu1, nu2, gamma)
+            mg.sync()
+            solve_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            line["solve"] = {"rtol": 1e-8, "cycles": k_cyc, "relres": relres, "ms": solve_ms, "ms_per_cycle": solve_ms / max(k_cyc, 1),
+                             "overhead_vs_isolated_cycle": solve_ms / max(k_cyc, 1) / isolated_ms - 1.0,
+                             "residual_history": [float(h) for h in hist],
+                             "factors": [float(hist[i + 1] / hist[i]) for i in range(len(hist) - 1) if hist[i] > 0]}
+        except Exception as ex:  # noqa: BLE001 - informational leg only
+            line["solve"] = {"error": str(ex)}
 
     # ---- N > 1: multi-GPU parity record + the same workload on ONE GPU (rank 0 alone), the strong-scaling denominator.
     #      Parity: from u = 0 on the same device-generated right-hand side, two single cycles and one 3-cycle run
     #      (mg_cycles: visit chains) on N ranks and on 1 rank; the iterates agree bit for bit iff the checksums do. ----
-    strong = None
     PAR = "u=0; 2 x mg_cycle; mg_cycles(3); 64-bit checksum of the owned rows (mg_checksum), summed over the ranks"
 
     def parity_run(m):
@@ -618,124 +692,103 @@ def run_ours(args, rank, world, local_rank):
         return m.checksum(level, 0)
 
     if world > 1 and not args.no_n1:
-        csum_n = sum_u64_over_ranks(parity_run(mg))
-        res = [None]
-        if rank == 0:
-            try:
-                mg1 = mgb200.Multigrid(level, dtype=dtype, smoother=smoother, device=local_rank, **flags)
-                csum_1 = parity_run(mg1)
-                mg1.time_cycle(level, nu1, nu2, gamma, W)
-                mg1.time_cycle(level, nu1, nu2, gamma, K)
-                ms1 = statistics.median([mg1.time_cycle(level, nu1, nu2, gamma, K) for _ in range(5)]) / K
-                mg1.time_cycle(level, nu1, nu2, gamma, 1)
-                iso1 = statistics.median([mg1.time_cycle(level, nu1, nu2, gamma, 1) for _ in range(9)])
-                mg1.close()
-                res[0] = {"workload": workload_name(level, args.dtype, nu1, nu2, gamma, smoother) + ", 1 GPU (rank 0 alone), same right-hand side",
-                          "n1_ms_per_step": ms1, "n1_value": upd / (ms1 * 1e-3), "n_gpus": world, "ms_per_step": ms_step,
-                          "speedup": ms1 / ms_step, "efficiency": ms1 / ms_step / world,
-                          "n1_isolated_cycle_ms": iso1, "isolated_cycle_ms": isolated_ms, "isolated_efficiency": iso1 / isolated_ms / world,
-                          "mgpu_parity": bool(csum_1 == csum_n), "parity_check": PAR,
-                          "checksum_1gpu": f"{csum_1:016x}", "checksum_ngpu": f"{csum_n:016x}"}
-            except Exception as ex:  # noqa: BLE001 - informational leg only
-                res[0] = {"error": str(ex)}
-        barrier()
-        strong = res[0]
+        with guard("strong_scaling"):
+            csum_n = sum_u64_over_ranks(parity_run(mg))
+            strong = None
+            if rank == 0:
+                try:
+                    mg1 = mgb200.Multigrid(level, dtype=dtype, smoother=smoother, device=local_rank, **flags)
+                    csum_1 = parity_run(mg1)
+                    mg1.time_cycle(level, nu1, nu2, gamma, W)
+                    mg1.time_cycle(level, nu1, nu2, gamma, K)
+                    ms1 = statistics.median([mg1.time_cycle(level, nu1, nu2, gamma, K) for _ in range(5)]) / K
+                    mg1.time_cycle(level, nu1, nu2, gamma, 1)
+                    iso1 = statistics.median([mg1.time_cycle(level, nu1, nu2, gamma, 1) for _ in range(9)])
+                    mg1.close()
+                    strong = {"workload": workload_name(level, args.dtype, nu1, nu2, gamma, smoother) + ", 1 GPU (rank 0 alone), same right-hand side",
+                              "n1_ms_per_step": ms1, "n1_value": upd / (ms1 * 1e-3), "n_gpus": world, "ms_per_step": ms_step,
+                              "speedup": ms1 / ms_step, "efficiency": ms1 / ms_step / world,
+                              "n1_isolated_cycle_ms": iso1, "isolated_cycle_ms": isolated_ms, "isolated_efficiency": iso1 / isolated_ms / world,
+                              "mgpu_parity": bool(csum_1 == csum_n), "parity_check": PAR,
+                              "checksum_1gpu": f"{csum_1:016x}", "checksum_ngpu": f"{csum_n:016x}"}
+                except Exception as ex:  # noqa: BLE001 - informational leg only
+                    strong = {"error": str(ex)}
+                line["strong_scaling"] = strong
+                line["n1_same_workload"] = ({"ms_per_step": strong["n1_ms_per_step"], "value": strong["n1_value"], "unit": UNIT,
+                                             "workload": strong["workload"]} if "n1_ms_per_step" in strong else strong)
+            barrier()
 
     # ---- N > 1: where the distributed cycle goes.  Device time per phase of the communication-avoiding plan from eagerly
     #      launched cycles with CUDA events around every op (mg_time_phases); per phase: max and mean over the ranks.
-    #      COLLECTIVE: every rank runs it (the cycles exchange halos), rank 0 reports ----
-    phases = None
+    #      COLLECTIVE: every rank runs it (the cycles exchange halos), rank 0 reports (eager launches were confirmed on the
+    #      hardware at 2 GPUs only, profiles/r02_scaling.md: hence the deadline) ----
     if world > 1 and not args.no_phases:
-        try:
-            ph = mg.time_phases(level, nu1, nu2, gamma, 5)
-        except Exception as ex:  # noqa: BLE001 - informational leg only
-            ph = {"error": str(ex)}
-        allp = [None] * world
-        dist.all_gather_object(allp, ph)
-        if all(p and "error" not in p for p in allp):
-            names = [k for k in allp[0] if k != "ops_per_cycle"]
-            tot = {k: [sum(p.get(k, {}).values()) for p in allp] for k in names}
-            phases = {"how": "5 eager (un-captured) cycles, CUDA events around every op of the communication-avoiding plan; "
-                             "includes the launch gaps of eager launches",
-                      "per_phase_max_over_ranks": {k: max(v) for k, v in tot.items()},
-                      "per_phase_mean_over_ranks": {k: sum(v) / world for k, v in tot.items()},
-                      "sum_of_phases_max_rank": max(sum(tot[k][r] for k in names) for r in range(world)),
-                      "rank0_by_level": {k: allp[0][k] for k in names},
-                      "captured_cycle_ms": isolated_ms}
-        else:
-            errs = [p.get("error") for p in allp if p and "error" in p]
-            phases = {"unavailable": errs[0] if errs else "this schedule does not run the communication-avoiding plan"}
+        with guard("phases_ms"):
+            try:
+                ph = mg.time_phases(level, nu1, nu2, gamma, 5)
+            except Exception as ex:  # noqa: BLE001 - informational leg only
+                ph = {"error": str(ex)}
+            allp = [None] * world
+            dist.all_gather_object(allp, ph)
+            if all(p and "error" not in p for p in allp):
+                names = [k for k in allp[0] if k != "ops_per_cycle"]
+                tot = {k: [sum(p.get(k, {}).values()) for p in allp] for k in names}
+                phases = {"how": "5 eager (un-captured) cycles, CUDA events around every op of the communication-avoiding plan; "
+                                 "includes the launch gaps of eager launches",
+                          "per_phase_max_over_ranks": {k: max(v) for k, v in tot.items()},
+                          "per_phase_mean_over_ranks": {k: sum(v) / world for k, v in tot.items()},
+                          "sum_of_phases_max_rank": max(sum(tot[k][r] for k in names) for r in range(world)),
+                          "rank0_by_level": {k: allp[0][k] for k in names},
+                          "captured_cycle_ms": isolated_ms}
+            else:
+                errs = [p.get("error") for p in allp if p and "error" in p]
+                phases = {"unavailable": errs[0] if errs else "this schedule does not run the communication-avoiding plan"}
+            line["phases_ms"] = phases
 
     # ---- N > 1: the weighted-Jacobi cycle on the same grid (round 1's scaling workload), timing only ----
-    extra = None
     if world > 1 and smoother != "jacobi" and not args.no_extra:
-        try:
-            mg.close()
-            mg = None
-            mgj = mgb200.Multigrid(level, dtype=dtype, smoother="jacobi", device=local_rank, rank=rank, world=world,
-                                   comm_id=new_comm_id(), agglomerate_level=args.aggl, **flags)
-            mgj.force_synthetic(SEED)
-            mgj.zero_u(level)
-            mgj.time_cycle(level, nu1, nu2, gamma, W)
-            mgj.time_cycle(level, nu1, nu2, gamma, K)
-            tj = []
-            for _ in range(7):
+        with guard("extra.jacobi_same_grid"):
+            try:
+                mg.close()
+                mg = None
+                mgj = mgb200.Multigrid(level, dtype=dtype, smoother="jacobi", device=local_rank, rank=rank, world=world,
+                                       comm_id=new_comm_id(), agglomerate_level=args.aggl, **flags)
+                mgj.force_synthetic(SEED)
+                mgj.zero_u(level)
+                mgj.time_cycle(level, nu1, nu2, gamma, W)
+                mgj.time_cycle(level, nu1, nu2, gamma, K)
+                tj = []
+                for _ in range(7):
+                    barrier()
+                    tj.append(max_over_ranks(mgj.time_cycle(level, nu1, nu2, gamma, K)))
+                msj = statistics.median(tj) / K
+                extra = {"jacobi_same_grid": {"workload": workload_name(level, args.dtype, nu1, nu2, gamma, "jacobi") + f", row slabs over {world} GPUs",
+                                              "ms_per_step": msj, "value": upd / (msj * 1e-3), "unit": UNIT}}
+                mgj.close()
+                if rank == 0 and not args.no_n1:
+                    mg1 = mgb200.Multigrid(level, dtype=dtype, smoother="jacobi", device=local_rank, **flags)
+                    mg1.force_synthetic(SEED)
+                    mg1.zero_u(level)
+                    mg1.time_cycle(level, nu1, nu2, gamma, W)
+                    mg1.time_cycle(level, nu1, nu2, gamma, K)
+                    ms1 = statistics.median([mg1.time_cycle(level, nu1, nu2, gamma, K) for _ in range(5)]) / K
+                    mg1.close()
+                    extra["jacobi_same_grid"].update({"n1_ms_per_step": ms1, "speedup": ms1 / msj, "efficiency": ms1 / msj / world})
                 barrier()
-                tj.append(max_over_ranks(mgj.time_cycle(level, nu1, nu2, gamma, K)))
-            msj = statistics.median(tj) / K
-            extra = {"jacobi_same_grid": {"workload": workload_name(level, args.dtype, nu1, nu2, gamma, "jacobi") + f", row slabs over {world} GPUs",
-                                          "ms_per_step": msj, "value": upd / (msj * 1e-3), "unit": UNIT}}
-            mgj.close()
-            if rank == 0 and not args.no_n1:
-                mg1 = mgb200.Multigrid(level, dtype=dtype, smoother="jacobi", device=local_rank, **flags)
-                mg1.force_synthetic(SEED)
-                mg1.zero_u(level)
-                mg1.time_cycle(level, nu1, nu2, gamma, W)
-                mg1.time_cycle(level, nu1, nu2, gamma, K)
-                ms1 = statistics.median([mg1.time_cycle(level, nu1, nu2, gamma, K) for _ in range(5)]) / K
-                mg1.close()
-                extra["jacobi_same_grid"].update({"n1_ms_per_step": ms1, "speedup": ms1 / msj, "efficiency": ms1 / msj / world})
-            barrier()
-        except Exception as ex:  # noqa: BLE001 - informational leg only
-            extra = {"jacobi_same_grid": {"error": str(ex)}}
+            except Exception as ex:  # noqa: BLE001 - informational leg only
+                extra = {"jacobi_same_grid": {"error": str(ex)}}
+            line["extra"] = extra
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64" if dtype == np.float64 else "f32", "data": "synthetic",
-            "config": {"workload": workload_name(level, args.dtype, nu1, nu2, gamma, smoother),
-                       "decomposition": "one GPU" if world == 1 else f"row slabs over {world} GPUs, halo exchange over NVLink (NCCL), coarse levels agglomerated",
-                       "level": level, "smoother": smoother, "rhs": rhs_desc, "updates_per_cycle": upd,
-                       "l2_policy": "inputs larger than L2 (4 arrays x %.0f MB on the finest level)" % (n * n * esize / 1e6),
-                       "regions": regions, "region_stat": "median",
-                       "agglomerate_level": mg.info(capi.MG_INFO_AGGLOMERATE_LEVEL, level) if (world > 1 and mg is not None) else (args.aggl or None),
-                       "timed_as": f"{K} consecutive cycles per region through mg_time_cycle (mg_cycles: POST of one cycle and PRE of "
-                                   f"the next are one launch on the finest level); isolated_cycle_ms = one mg_cycle at a time",
-                       "scaling_note": ("N=1 measures BASELINE configs[1] (4097^2 Jacobi), N>1 measures configs[2] (16385^2 RB-GS): "
-                                        "same-workload speed-up / efficiency are in strong_scaling, not in value(N)/value(1)"),
-                       "env_knobs": {k: v for k, v in sorted(os.environ.items()) if k.startswith("MGB200_")},
-                       "flags": flags},
-            "isolated_cycle_ms": isolated_ms,
-            "finest_points_per_s": n * n / (ms_step * 1e-3),
-            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-    line["solve"] = solve_info
-    if phases is not None:
-        line["phases_ms"] = phases
-    if strong is not None:
-        line["strong_scaling"] = strong
-        line["n1_same_workload"] = ({"ms_per_step": strong["n1_ms_per_step"], "value": strong["n1_value"], "unit": UNIT,
-                                     "workload": strong["workload"]} if "n1_ms_per_step" in strong else strong)
-    if extra is not None:
-        line["extra"] = extra
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_vcycle_rate(level, nu1, nu2, steps=3, warmup=1, smoother=1 if rb else 0, gamma=gamma,
                                                with_csr=True, with_as_written=True)
     if mg is not None:
         mg.close()
-    if rank == 0:
-        print(json.dumps(line), flush=True)
+    guard.print_final()
     if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+        with guard("teardown"):
+            dist.barrier()
+            dist.destroy_process_group()
 
 
 def run_micro(args, rank, world, local_rank):
@@ -827,6 +880,8 @@ def main():
     ap.add_argument("--no-n1", action="store_true", help="N>1: skip the single-GPU run of the same workload on rank 0 (strong_scaling, mgpu_parity)")
     ap.add_argument("--no-phases", action="store_true", help="N>1: skip the per-phase timing of the distributed cycle")
     ap.add_argument("--no-extra", action="store_true", help="N>1: skip the extra weighted-Jacobi timing on the same grid")
+    ap.add_argument("--leg-timeout", type=float, default=150.0,
+                    help="N>1: seconds an informational (collective) leg may take before the line is printed without it")
     ap.add_argument("--micro", action="store_true",
                     help="BASELINE configs[4]: smoother/residual micro-benchmark (default 32769^2; use --dtype f32)")
     ap.add_argument("--full-host-vectors", action="store_true",

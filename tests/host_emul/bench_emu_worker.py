@@ -42,7 +42,7 @@ def main():
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     args = argparse.Namespace(gpus=world, steps=3, warmup=1, impl="ours", level=a.level, dtype=a.dtype, smoother=a.smoother,
                               nu1=2, nu2=2, gamma=a.gamma, no_graph=False, no_fused=False, no_tail=False, no_cpu=True,
-                              aggl=a.aggl, no_e2e=False, full_host_vectors=False, no_n1=False, no_extra=False, no_phases=False, micro=a.micro)
+                              aggl=a.aggl, no_e2e=False, full_host_vectors=False, no_n1=False, no_extra=False, no_phases=False, micro=a.micro, leg_timeout=120.0)
     if a.micro:
         bench.run_micro(args, rank, world, 0)
     else:

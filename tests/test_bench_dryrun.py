@@ -101,7 +101,7 @@ class StubMG:
 def _args(**kw):
     d = dict(gpus=1, steps=3, warmup=1, impl="ours", level=6, dtype="f64", smoother="jacobi", nu1=2, nu2=2, gamma=1,
              no_graph=False, no_fused=False, no_tail=False, no_cpu=True, aggl=0, no_e2e=False, full_host_vectors=False, no_n1=False,
-             no_extra=False, no_phases=False, micro=False)
+             no_extra=False, no_phases=False, micro=False, leg_timeout=120.0)
     d.update(kw)
     return argparse.Namespace(**d)
 
@@ -220,3 +220,39 @@ def test_gpu_local_affinity_binds_and_restores(monkeypatch):
     fake.nvmlDeviceGetCpuAffinity = lambda h, n: (_ for _ in ()).throw(RuntimeError("no NVML"))
     with bench.GpuLocalAffinity(0) as a:
         assert os.sched_getaffinity(0) == before and a.cpus is None
+
+
+def test_leg_guard_prints_the_core_line_when_a_collective_leg_stalls():
+    """bench.LegGuard: a leg that does not come back within its budget costs that leg, not the record -- rank 0 prints
+    the line as it stands with `aborted_leg`, every rank exits 0; a finished leg disarms its deadline."""
+    import subprocess
+    import sys
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prog = ("import sys, time, json; sys.path.insert(0, %r); import bench\n"
+            "line = {'metric': bench.METRIC, 'value': 1.0}\n"
+            "g = bench.LegGuard(int(sys.argv[1]), line, enabled=True, budget_s=0.3)\n"
+            "with g('quick'):\n    line['quick'] = True\n"
+            "time.sleep(0.5)\n"                     # the disarmed deadline of 'quick' must not fire here
+            "with g('stalled'):\n    time.sleep(30)\n"
+            "print('NOT REACHED')\n") % root
+    for rank in (0, 1):
+        p = subprocess.run([sys.executable, "-c", prog, str(rank)], capture_output=True, text=True, timeout=25)
+        assert p.returncode == 0, p.stderr
+        assert "NOT REACHED" not in p.stdout
+        if rank == 0:
+            d = json.loads(p.stdout.strip().splitlines()[-1])
+            assert d["value"] == 1.0 and d["quick"] is True and d["aborted_leg"]["leg"] == "stalled"
+        else:
+            assert p.stdout.strip() == ""
+    # not enabled (N = 1): no deadline, one final line, print_final only once
+    line = {"metric": bench.METRIC}
+    g = bench.LegGuard(0, line, enabled=False, budget_s=0.01)
+    with g("leg"):
+        import time
+        time.sleep(0.05)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        g.print_final()
+        g.print_final()
+    assert len(buf.getvalue().strip().splitlines()) == 1 and "aborted_leg" not in line
