@@ -671,8 +671,12 @@ static void comm_avoid_run(Ctx& ctx, const SchedPlan& plan, int nu1, int nu2)
     for (const SchedOp& op : plan.ops) {
         // mg_time_phases: a pair of events around every op of the plan (eager launches only; see Ctx::time_phases)
         const bool timed = ctx.phase_on && !ctx.capturing;
-        PhaseRec rec;
+        size_t slot = 0;
         if (timed) {
+            // the record is in the log before its events exist: whatever throws below, Ctx::time_phases destroys them
+            slot = ctx.phase_log.size();
+            ctx.phase_log.emplace_back();
+            PhaseRec& rec = ctx.phase_log.back();
             rec.kind = op.kind;
             rec.level = op.level;
             MG_CK(cudaEventCreate(&rec.e0));
@@ -680,10 +684,7 @@ static void comm_avoid_run(Ctx& ctx, const SchedPlan& plan, int nu1, int nu2)
             MG_CK(cudaEventRecord(rec.e0, ctx.stream));
         }
         comm_avoid_op<T>(ctx, plan, op, nu1, nu2);
-        if (timed) {
-            MG_CK(cudaEventRecord(rec.e1, ctx.stream));
-            ctx.phase_log.push_back(rec);
-        }
+        if (timed) MG_CK(cudaEventRecord(ctx.phase_log[slot].e1, ctx.stream));
     }
 }
 
