@@ -63,7 +63,8 @@ class Jobs:
     def start(self):
         self.procs = {}
         jobs = {
-            "parity": (pytest_cmd(["tests/test_parity_gpu.py", "-k",
+            # the long pole of the file: three xdist workers (the other jobs are short and leave cores free)
+            "parity": (pytest_cmd(["-n", "3", "tests/test_parity_gpu.py", "-k",
                                    "not 4097 and not cpp_ and not combinations[9- and not 10-float and not iterates_bitwise[9 "
                                    "and not zero_guess and not visit_chain"]), {}),
             "chains": (pytest_cmd(["tests/test_parity_gpu.py", "-k",
