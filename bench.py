@@ -149,10 +149,15 @@ class LegGuard:
             self._timer.start()
         return self
 
-    def __exit__(self, *a):
+    def __exit__(self, etype, exc, tb):
         if self._timer is not None:
             self._timer.cancel()
             self._timer = None
+        if exc is not None and isinstance(exc, Exception):
+            # an informational leg must not take the core measurement down with it: note the error, go on (if the other
+            # ranks are now waiting for this one inside a collective, the next leg's deadline ends the job cleanly)
+            self.line.setdefault("leg_errors", {})[self._name] = f"{etype.__name__}: {exc}"
+            return True
         return False
 
     def print_final(self):

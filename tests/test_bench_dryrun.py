@@ -256,3 +256,16 @@ def test_leg_guard_prints_the_core_line_when_a_collective_leg_stalls():
         g.print_final()
         g.print_final()
     assert len(buf.getvalue().strip().splitlines()) == 1 and "aborted_leg" not in line
+
+
+def test_leg_guard_records_an_exception_and_goes_on():
+    line = {}
+    g = bench.LegGuard(0, line, enabled=True, budget_s=30.0)
+    with g("broken"):
+        raise RuntimeError("boom")
+    with g("fine"):
+        line["fine"] = 1
+    assert line["leg_errors"] == {"broken": "RuntimeError: boom"} and line["fine"] == 1
+    with pytest.raises(KeyboardInterrupt):
+        with g("interrupted"):
+            raise KeyboardInterrupt()
