@@ -71,6 +71,10 @@ int mg_create(mg_ctx** out, const mg_config* cfg)
         std::lock_guard<std::mutex> lk(g_mu);
         g_create_error = e.what();
         return MG_ERR_STATE;
+    } catch (...) {   // nothing may cross the C boundary
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_create_error = "unknown error";
+        return MG_ERR_STATE;
     }
 }
 
@@ -97,6 +101,8 @@ int mg_comm_id(void* out128)
     } catch (const std::exception& e) {
         std::lock_guard<std::mutex> lk(g_mu);
         g_create_error = e.what();
+        return MG_ERR_COMM;
+    } catch (...) {
         return MG_ERR_COMM;
     }
 }
