@@ -166,8 +166,10 @@ def test_bench_harness_end_to_end_under_emulation(jobs, name):
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
     assert d["roofline"]["achieved"] > 0 and set(["bound", "peak", "unit", "frac", "traffic"]) <= set(d["roofline"])
     assert d["solve"]["cycles"] > 0 and d["solve"]["relres"] <= 1e-8 and len(d["solve"]["residual_history"]) == d["solve"]["cycles"] + 1
+    assert "aborted_leg" not in d and "leg_errors" not in d, (d.get("aborted_leg"), d.get("leg_errors"))   # bench.LegGuard
     if world > 1:   # the strong-scaling denominator: same grid on one rank
         assert d["n1_same_workload"]["ms_per_step"] > 0 and "error" not in d["n1_same_workload"]
+        assert d["strong_scaling"]["mgpu_parity"] is True and "phases_ms" in d
 
 
 def test_smoke_entry_under_emulation():
