@@ -95,10 +95,21 @@ inline int level_of_size(std::size_t size)
     return l;
 }
 
+// the C ABI takes bare pointers: the length of every vector handed over is checked here against its level
+inline void require_level_size(std::size_t size, int lvl, const char* what)
+{
+    const long long n = mg_level_side(lvl);
+    if (n < 0 || size != (std::size_t)n * (std::size_t)n)
+        throw std::runtime_error(std::string(what) + ": vector length " + std::to_string(size) + " is not (2^" +
+                                 std::to_string(lvl) + "-1)^2");
+}
+
 // P:125-147.  Like the reference, v is smoothed in place AND returned by value (P:146).
 template <typename T>
 std::vector<T> jacobirelaxation(queue<T>& q, level a_h, std::vector<T>& v, std::vector<T>& fh, const int& mu)
 {
+    require_level_size(v.size(), a_h.index, "jacobirelaxation: v");
+    require_level_size(fh.size(), a_h.index, "jacobirelaxation: fh");
     q.check(mg_host_jacobirelaxation(q.handle(), a_h.index, v.data(), fh.data(), mu), "jacobirelaxation");
     return v;
 }
@@ -129,6 +140,8 @@ std::vector<T> interpolation2d(queue<T>& q, std::vector<T>& vec_2h)
 template <typename T>
 std::vector<T> vcyclemultigrid(queue<T>& q, level a_h, std::vector<T>& vec_h, std::vector<T>& f_h)
 {
+    require_level_size(vec_h.size(), a_h.index, "vcyclemultigrid: vec_h");
+    require_level_size(f_h.size(), a_h.index, "vcyclemultigrid: f_h");
     std::vector<T> out(vec_h);
     q.check(mg_host_vcyclemultigrid(q.handle(), a_h.index, out.data(), f_h.data(), q.par.mu1, q.par.mu2, q.par.gamma),
             "vcyclemultigrid");
@@ -140,6 +153,7 @@ template <typename T>
 std::vector<T> fullmultigrid(queue<T>& q, level a_h, std::vector<T>& f_h)
 {
     if (a_h.index != q.par.finest_level) throw std::runtime_error("fullmultigrid starts on the finest level");
+    require_level_size(f_h.size(), a_h.index, "fullmultigrid: f_h");
     std::vector<T> out(f_h.size(), 0);
     q.check(mg_host_fullmultigrid(q.handle(), f_h.data(), out.data(), q.par.mu0 + 1, q.par.mu1, q.par.mu2), "fullmultigrid");
     return out;
@@ -210,6 +224,8 @@ struct ProblemVar {
 template <typename T>
 void jacobirelaxation(queue<T>& q, std::vector<T>& vec, std::vector<T>& b, ProblemVar<T>& obj, int current_level)
 {
+    require_level_size(vec.size(), current_level, "jacobirelaxation: vec");
+    require_level_size(b.size(), current_level, "jacobirelaxation: b");
     q.check(mg_host_jacobirelaxation(q.handle(), current_level, vec.data(), b.data(), obj.par.mu1), "jacobirelaxation");
 }
 
@@ -217,6 +233,8 @@ void jacobirelaxation(queue<T>& q, std::vector<T>& vec, std::vector<T>& b, Probl
 template <typename T>
 std::vector<T> vcyclemultigrid(queue<T>& q, ProblemVar<T>& obj, std::vector<T>& vec_h, std::vector<T>& f_h, int current_level)
 {
+    require_level_size(vec_h.size(), current_level, "vcyclemultigrid: vec_h");
+    require_level_size(f_h.size(), current_level, "vcyclemultigrid: f_h");
     std::vector<T> out(vec_h);
     q.check(mg_host_vcyclemultigrid(q.handle(), current_level, out.data(), f_h.data(), obj.par.mu1, obj.par.mu2, obj.par.gamma),
             "vcyclemultigrid");
@@ -229,17 +247,24 @@ std::vector<T> fullmultigrid(queue<T>& q, ProblemVar<T>& obj, std::vector<T>& f_
 {
     mg_ctx* c = q.handle();
     const int lo = obj.par.coarsest_level;
+    require_level_size(f_h.size(), current_level, "fullmultigrid: f_h");
     q.check(mg_set_rhs_host(c, current_level, f_h.data()), "fullmultigrid: f_h");
     for (int l = current_level - 1; l >= lo; --l) {
         auto it = obj.b_dict.find(l);
-        if (it != obj.b_dict.end()) q.check(mg_set_rhs_host(c, l, it->second.data()), "fullmultigrid: b_dict");
-        else q.check(mg_restrict_rhs(c, l + 1), "fullmultigrid: restrict");
+        if (it != obj.b_dict.end()) {
+            require_level_size(it->second.size(), l, "fullmultigrid: b_dict");
+            q.check(mg_set_rhs_host(c, l, it->second.data()), "fullmultigrid: b_dict");
+        } else {
+            q.check(mg_restrict_rhs(c, l + 1), "fullmultigrid: restrict");
+        }
     }
     q.check(mg_zero_u(c, lo), "fullmultigrid");                                              // M:176
-    for (int i = 0; i <= obj.par.mu0; ++i) q.check(mg_cycle(c, lo, obj.par.mu1, obj.par.mu2, 1), "fullmultigrid");
+    // the loop `for i <= mu0: vec_h = vcyclemultigrid(...)` (M:186-188; P:646-648) as ONE call per level: same bits as mu0+1
+    // mg_cycle calls, and the library may keep the iterate on chip between consecutive cycles (visit chains)
+    q.check(mg_cycles(c, lo, obj.par.mu1, obj.par.mu2, 1, obj.par.mu0 + 1), "fullmultigrid");
     for (int l = lo + 1; l <= current_level; ++l) {
         q.check(mg_prolong_set(c, l), "fullmultigrid: interpolation");                       // M:185
-        for (int i = 0; i <= obj.par.mu0; ++i) q.check(mg_cycle(c, l, obj.par.mu1, obj.par.mu2, 1), "fullmultigrid");
+        q.check(mg_cycles(c, l, obj.par.mu1, obj.par.mu2, 1, obj.par.mu0 + 1), "fullmultigrid");
     }
     const std::size_t n = (std::size_t)mg_level_side(current_level);
     std::vector<T> vec_h(n * n, 0);

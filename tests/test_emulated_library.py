@@ -204,3 +204,32 @@ def test_problemvar_example_under_emulation(tmp_path, emulated_library):
 def test_problem_setup_gpu_tests_under_emulation(jobs):
     out = jobs.result("problem")
     assert " passed" in out and "failed" not in out
+
+
+def test_cpp_driver_rejects_vectors_of_the_wrong_length(tmp_path, emulated_library):
+    """include/mgb200_driver.hpp: the C ABI takes bare pointers, so the std::vector wrappers check every length against
+    its level before the call (a short vector would otherwise be read past its end by the copy)."""
+    libdir = os.path.dirname(emulated_library)
+    src = tmp_path / "badsize.cpp"
+    src.write_text('''
+#include <cstdio>
+#include "mgb200_driver.hpp"
+int main() {
+    mgb200::parameters p; p.finest_level = 5; p.coarsest_level = 1; p.mu0 = 1; p.mu1 = 2; p.mu2 = 2;
+    mgb200::queue<double> q(p);
+    std::vector<double> f = mgb200::globalforcefunction(q), u(f.size(), 0.0), small(10, 0.0);
+    int caught = 0;
+    try { mgb200::vcyclemultigrid(q, q.finest(), small, f); } catch (const std::runtime_error&) { ++caught; }
+    try { mgb200::vcyclemultigrid(q, q.finest(), u, small); } catch (const std::runtime_error&) { ++caught; }
+    try { mgb200::jacobirelaxation(q, q[4], u, f, 2); } catch (const std::runtime_error&) { ++caught; }   // level 4 != 31^2
+    try { mgb200::fullmultigrid(q, q.finest(), small); } catch (const std::runtime_error&) { ++caught; }
+    std::vector<double> ok = mgb200::vcyclemultigrid(q, q.finest(), u, f);      // and the context still works
+    std::printf("caught=%d size=%zu\\n", caught, ok.size());
+    return (caught == 4 && ok.size() == f.size()) ? 0 : 1;
+}
+''')
+    exe = str(tmp_path / "badsize")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe, "-L" + libdir,
+                    "-lmgb200_emu", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "caught=4 size=961" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
