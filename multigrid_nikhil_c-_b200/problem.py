@@ -83,12 +83,12 @@ def fullmultigrid(mg: Multigrid, obj: ProblemVar, level: Optional[int] = None) -
         else:
             mg.restrict_rhs(l + 1)
     mg.zero_u(obj.coarsest_level)                          # M:176
-    for _ in range(obj.mu0 + 1):
-        mg.cycle(obj.coarsest_level, obj.mu1, obj.mu2, 1)  # coarsest level: direct solve (M:137) or nu1 + nu2 sweeps (P:583-587)
+    # mu0+1 consecutive cycles per level as ONE mg_cycles call: the same bits as mu0+1 mg_cycle calls, and the library
+    # may fuse the post-smoothing of one cycle with the pre-smoothing of the next (visit chains)
+    mg.cycles(obj.mu0 + 1, obj.coarsest_level, obj.mu1, obj.mu2, 1)   # coarsest level: direct solve (M:137) or nu1 + nu2 sweeps (P:583-587)
     for l in range(obj.coarsest_level + 1, top + 1):
         mg.prolong_set(l)                                  # M:185
-        for _ in range(obj.mu0 + 1):                       # M:186-188
-            mg.cycle(l, obj.mu1, obj.mu2, 1)
+        mg.cycles(obj.mu0 + 1, l, obj.mu1, obj.mu2, 1)     # M:186-188
     return mg.get_u(top)
 
 
